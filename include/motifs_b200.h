@@ -1,0 +1,126 @@
+/* motifs_b200.h — C ABI of libmotifs_b200.so (sm_100a kernels for the neural-motifs hot path).
+ *
+ * Every entry point takes plain pointers, sizes and a cudaStream_t; no torch types.
+ * Device pointers are marked DEV, host pointers HOST.  Unless noted, the caller owns and
+ * allocates every buffer (inputs, outputs and scratch), exactly as the reference's callers
+ * do (SURVEY.md §8b "Ownership").
+ *
+ * Return convention (superset of the reference's): 1 = ok (what the reference launchers
+ * return), 0 = bad argument (roi_align_cuda.c:19-22), negative = CUDA failure or
+ * unsupported shape; mb200_last_error() returns the message.  Nothing calls exit() or
+ * prints, unlike roi_align_kernel.cu:94-98 / highway_lstm_kernel.cu:17-29.
+ *
+ * PART 1 keeps the reference's own launcher names and argument order (drop-in symbols).
+ * PART 2 are new entry points (prefix mb200_) the B200 host code uses.
+ */
+#ifndef MOTIFS_B200_H_
+#define MOTIFS_B200_H_
+
+#include <cuda_runtime_api.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------ PART 1: drop-in symbols */
+
+/* replaces lib/fpn/roi_align/src/cuda/roi_align_kernel.h:11-15 (roi_align_kernel.cu:82-101).
+ * image DEV [batch,depth,H,W] fp32; boxes DEV [num_boxes,5] = (batch idx, x1,y1,x2,y2) with the
+ * corners already normalised by (W-1)/scale, (H-1)/scale (functions/roi_align.py:25-31);
+ * crops DEV [num_boxes,depth,crop_h,crop_w]. Every element of crops is written. */
+int ROIAlignForwardLaucher(const float* image_ptr, const float* boxes_ptr, int num_boxes, int batch,
+                           int image_height, int image_width, int crop_height, int crop_width,
+                           int depth, float extrapolation_value, float* crops_ptr, cudaStream_t stream);
+
+/* replaces roi_align_kernel.h:21-23 (roi_align_kernel.cu:172-191). grads_image DEV
+ * [batch,depth,H,W] must be zeroed by the caller; gradients are accumulated atomically. */
+int ROIAlignBackwardLaucher(const float* grads_ptr, const float* boxes_ptr, int num_boxes, int batch,
+                            int image_height, int image_width, int crop_height, int crop_width,
+                            int depth, float* grads_image_ptr, cudaStream_t stream);
+
+/* replaces lib/fpn/nms/src/cuda/nms_kernel.h:1-2 (nms_kernel.cu:88-131). keep_out HOST
+ * [boxes_num] int32; boxes_dev DEV [boxes_num,4] sorted by descending score. Returns the
+ * number of kept boxes (>= 0) or a negative error. Synchronous, like the reference. */
+int ApplyNMSGPU(int* keep_out, const float* boxes_dev, const int boxes_num, float nms_overlap_thresh,
+                int device_id);
+
+/* replaces lib/lstm/highway_lstm_cuda/src/highway_lstm_kernel.h:7 (highway_lstm_kernel.cu:377-496).
+ * Same argument order. lengths HOST [miniBatch] int32, sorted descending. `handle` is accepted
+ * for ABI compatibility and ignored (no cuBLAS is used). Buffers as in
+ * alternating_highway_lstm.py:71-107: x [T,B,In]; h_data,c_data [L,T+1,B,H] zero-initialised;
+ * tmp_i [B,6H], tmp_h [B,5H] (unused scratch, may be NULL); T flat weights; bias [L,5H];
+ * dropout [L,B,H]; gates [L,T,B,6H] or NULL when !is_training. Asynchronous on `stream`. */
+void highway_lstm_forward_ongpu(int inputSize, int hiddenSize, int miniBatch, int numLayers, int seqLength,
+                                float* x, int* lengths, float* h_data, float* c_data, float* tmp_i,
+                                float* tmp_h, float* T, float* bias, float* dropout, float* gates,
+                                int is_training, cudaStream_t stream, void* handle);
+
+/* replaces highway_lstm_kernel.h:9 (highway_lstm_kernel.cu:162-375). Same argument order.
+ * T_grad and bias_grad are ACCUMULATED into (caller pre-zeroes), as the reference's beta=1 GEMMs. */
+void highway_lstm_backward_ongpu(int inputSize, int hiddenSize, int miniBatch, int numLayers, int seqLength,
+                                 float* out_grad, int* lengths, float* h_data_grad, float* c_data_grad,
+                                 float* x, float* h_data, float* c_data, float* T, float* gates_out,
+                                 float* dropout_in, float* h_gates_grad, float* i_gates_grad,
+                                 float* h_out_grad, float* x_grad, float* T_grad, float* bias_grad,
+                                 int isTraining, int do_weight_grad, cudaStream_t stream, void* handle);
+
+/* ------------------------------------------------------------------ PART 2: mb200_ entry points */
+
+const char* mb200_last_error(void);
+int mb200_abi_version(void);
+int mb200_compiled_arch(void);
+int mb200_device_ok(void);
+
+/* RoIAlign, NHWC feature map in -> [num_boxes, crop_h*crop_w, depth] out (bin-major,
+ * channel-minor). Same sampling as ROIAlignForwardLaucher. */
+int mb200_roi_align_forward_nhwc(const float* image_nhwc, const float* boxes_ptr, int num_boxes, int batch,
+                                 int image_height, int image_width, int crop_height, int crop_width,
+                                 int depth, float extrapolation_value, float* crops_nhwc, cudaStream_t stream);
+
+/* Segmented greedy NMS entirely on the device (no D2H). See csrc/nms.cu. */
+long long mb200_nms_mask_words(const int* seg_sizes_host, int num_segments);
+int mb200_nms_segmented(const float* boxes_dev, const int* seg_off_dev, const long long* mask_off_dev,
+                        int num_segments, int max_seg, float thresh, int max_keep,
+                        unsigned long long* mask_dev, int* keep_dev, int* num_keep_dev, cudaStream_t stream);
+
+/* replaces lib/fpn/box_utils.py:109-131 (fp32 IoU) on the device. out DEV [A,B]. */
+int mb200_bbox_overlaps_f32(const float* boxes_a, int A, const float* boxes_b, int B, float* out,
+                            cudaStream_t stream);
+/* replaces lib/fpn/box_intersections_cpu/bbox.pyx:15-62 (mode 0) and :64-107 (mode 1), float64. */
+int mb200_bbox_overlaps_f64(const double* boxes, int N, const double* query, int K, int mode, double* out,
+                            cudaStream_t stream);
+/* replaces lib/get_union_boxes.py:82-87 (union roi) and the pair gather of :47. */
+int mb200_union_rois(const float* rois, const long long* pairs, int num_pairs, float* union_rois,
+                     float* pair_boxes, cudaStream_t stream);
+/* replaces lib/draw_rectangles/draw_rectangles.pyx:12-67; out DEV [N,2,P,P] = mask - offset. */
+int mb200_draw_union_boxes(const float* pair_boxes, int num_pairs, int pooling_size, float offset, float* out,
+                           cudaStream_t stream);
+/* replaces lib/fpn/box_utils.py:28-48 (+ the clamps of object_detector.py:383-387). */
+int mb200_bbox_preds(const float* boxes, const float* deltas, long long num_rows, int rows_per_box,
+                     const float* im_hw, const int* im_idx, float* out, cudaStream_t stream);
+
+/* Highway LSTM with DEVICE lengths and caller-provided scratch (what the torch host code calls;
+ * the drop-in launchers above wrap these). See csrc/lstm.cu. proj_scratch / dG_scratch are
+ * mb200_highway_lstm_scratch_floats() floats. */
+size_t mb200_highway_lstm_scratch_floats(int hiddenSize, int miniBatch, int seqLength);
+int mb200_highway_lstm_forward(int inputSize, int hiddenSize, int miniBatch, int numLayers, int seqLength,
+                               const float* x, const int* lengths_dev, float* h_data, float* c_data,
+                               const float* T, const float* bias, const float* dropout, float* gates,
+                               float* proj_scratch, cudaStream_t stream);
+int mb200_highway_lstm_backward(int inputSize, int hiddenSize, int miniBatch, int numLayers, int seqLength,
+                                const float* out_grad, const int* lengths_dev, float* h_data_grad,
+                                float* c_data_grad, const float* x, const float* h_data, const float* c_data,
+                                const float* T, const float* gates_out, const float* dropout_in,
+                                float* h_out_grad, float* x_grad, float* T_grad, float* bias_grad,
+                                int do_weight_grad, float* dG_scratch, cudaStream_t stream);
+
+/* Exact-fp32 SIMT GEMM, row-major, C = alpha*op(A)*op(B) + beta*C (replaces the cublasSgemm calls
+ * of highway_lstm_kernel.cu:441-465 for small shapes; cross-check for the tcgen05 path). */
+int mb200_sgemm(int transA, int transB, int M, int N, int K, float alpha, const float* A, int lda,
+                const float* B, int ldb, float beta, float* C, int ldc, cudaStream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOTIFS_B200_H_ */

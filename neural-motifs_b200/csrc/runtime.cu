@@ -1,0 +1,31 @@
+// Error bookkeeping and version probe for libmotifs_b200.so.
+#include "common.cuh"
+#include <string.h>
+
+static thread_local char g_err[512] = "";
+
+void mb200_set_error(const char* what, cudaError_t err) {
+  snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(err));
+}
+
+extern "C" {
+
+const char* mb200_last_error() { return g_err; }
+
+// ABI version of include/motifs_b200.h this library implements.
+int mb200_abi_version() { return 1; }
+
+// Compiled architecture (100 => sm_100a). Lets the host fail loudly on a mismatched device.
+int mb200_compiled_arch() { return 100; }
+
+// Returns 1 when the current device is a compute-capability 10.x part, 0 otherwise,
+// MB200_ERR_CUDA when no device is usable.
+int mb200_device_ok() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return MB200_ERR_CUDA;
+  cudaDeviceProp p;
+  if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) return MB200_ERR_CUDA;
+  return p.major == 10 ? 1 : 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,94 @@
+"""ctypes binding of libmotifs_b200.so (the C ABI declared in include/motifs_b200.h).
+
+The product path has NO fallback: if the shared library is missing, was built for another
+architecture, or a call fails, an exception is raised.  Nothing here imports `oracle/`.
+"""
+import ctypes
+import os
+from ctypes import c_int, c_float, c_void_p, c_longlong, c_size_t, c_char_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libmotifs_b200.so")
+
+P = c_void_p  # every device / host pointer crosses the boundary as a raw address
+
+# name -> (restype, argtypes); mirrors include/motifs_b200.h one to one.
+SIGNATURES = {
+    "ROIAlignForwardLaucher": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, P, P]),
+    "ROIAlignBackwardLaucher": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P]),
+    "ApplyNMSGPU": (c_int, [P, P, c_int, c_float, c_int]),
+    "highway_lstm_forward_ongpu": (None, [c_int] * 5 + [P] * 10 + [c_int, P, P]),
+    "highway_lstm_backward_ongpu": (None, [c_int] * 5 + [P] * 16 + [c_int, c_int, P, P]),
+    "mb200_last_error": (c_char_p, []),
+    "mb200_abi_version": (c_int, []),
+    "mb200_compiled_arch": (c_int, []),
+    "mb200_device_ok": (c_int, []),
+    "mb200_roi_align_forward_nhwc": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, P, P]),
+    "mb200_nms_mask_words": (c_longlong, [P, c_int]),
+    "mb200_nms_segmented": (c_int, [P, P, P, c_int, c_int, c_float, c_int, P, P, P, P]),
+    "mb200_bbox_overlaps_f32": (c_int, [P, c_int, P, c_int, P, P]),
+    "mb200_bbox_overlaps_f64": (c_int, [P, c_int, P, c_int, c_int, P, P]),
+    "mb200_union_rois": (c_int, [P, P, c_int, P, P, P]),
+    "mb200_draw_union_boxes": (c_int, [P, c_int, c_int, c_float, P, P]),
+    "mb200_bbox_preds": (c_int, [P, P, c_longlong, c_int, P, P, P, P]),
+    "mb200_highway_lstm_scratch_floats": (c_size_t, [c_int, c_int, c_int]),
+    "mb200_highway_lstm_forward": (c_int, [c_int] * 5 + [P] * 9 + [P]),
+    "mb200_highway_lstm_backward": (c_int, [c_int] * 5 + [P] * 14 + [c_int, P, P]),
+    "mb200_sgemm": (c_int, [c_int, c_int, c_int, c_int, c_int, c_float, P, c_int, P, c_int, c_float, P, c_int, P]),
+}
+
+_lib = None
+
+
+class MotifsB200Error(RuntimeError):
+    pass
+
+
+def load():
+    """Load (once) and return the ctypes handle; raises MotifsB200Error if it cannot."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise MotifsB200Error(
+            "libmotifs_b200.so not found at %s — run `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(there is no CPU or library fallback)" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError as e:
+            raise MotifsB200Error("libmotifs_b200.so does not export %s" % name) from e
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def last_error():
+    return load().mb200_last_error().decode()
+
+
+def check(rc, what):
+    """The launchers return 1 on success (reference convention); anything else raises."""
+    if rc != 1:
+        raise MotifsB200Error("%s failed (code %d): %s" % (what, rc, last_error()))
+
+
+def ptr(t):
+    """Raw address of a torch tensor (or None)."""
+    if t is None:
+        return None
+    return c_void_p(t.data_ptr())
+
+
+def cur_stream():
+    import torch
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise MotifsB200Error("motifs_b200 operators run on CUDA tensors only (got a %s tensor); "
+                                  "there is no CPU path" % t.device)
