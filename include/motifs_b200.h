@@ -120,6 +120,30 @@ int mb200_highway_lstm_backward(int inputSize, int hiddenSize, int miniBatch, in
 int mb200_sgemm(int transA, int transB, int M, int N, int K, float alpha, const float* A, int lda,
                 const float* B, int ldb, float beta, float* C, int ldc, cudaStream_t stream);
 
+/* ---- bf16x3 tensor-core path (csrc/gemm_tc.cu, csrc/convert.cu): tcgen05.mma + TMA.
+ * Operands are (hi, lo) bf16 pairs, K contiguous, row pitch Kp % 64 == 0, zero padded. */
+
+/* replaces cublasSgemm under nn.Linear (lib/object_detector.py:102-103, lib/rel_model.py:360-390):
+ * C[M,N] = A[M,K] * B[N,K]^T (+ bias[N]) (ReLU). Outputs C fp32 (ldc) and/or (Chi,Clo) (ldsplit). */
+long long mb200_gemm_workspace_floats(int M, int N, int Kp);
+int mb200_gemm_bf16x3(const void* Ahi, const void* Alo, const void* Bhi, const void* Blo, int M, int N, int Kp,
+                      const float* bias, int relu, float* C, long long ldc, void* Chi, void* Clo,
+                      long long ldsplit, float* workspace, cudaStream_t stream);
+/* replaces cuDNN under the 3x3/pad-1 VGG convolutions (lib/object_detector.py:110-127):
+ * x NHWC pair [B,H,W,Cin], w [Cout, 9*Cin] pair in (kh,kw,cin) order, y NHWC fp32 and/or pair. */
+int mb200_conv3x3_bf16x3(const void* xhi, const void* xlo, const void* whi, const void* wlo, int B, int H, int W,
+                         int Cin, int Cout, const float* bias, int relu, float* y, void* yhi, void* ylo,
+                         cudaStream_t stream);
+int mb200_split_bf16(const float* src, long long rows, int cols, long long ld, int Kp, void* hi, void* lo,
+                     cudaStream_t stream);
+int mb200_split_transpose_bf16(const float* src, int rows, int cols, long long ld, int Rp, void* hi, void* lo,
+                               cudaStream_t stream);
+int mb200_conv_weight_split(const float* w_oihw, int O, int I, int Ip, void* hi, void* lo, cudaStream_t stream);
+int mb200_im2col3_split(const float* x_nchw, int B, int H, int W, void* hi, void* lo, cudaStream_t stream);
+int mb200_stem_weight_split(const float* w_oihw, int O, void* hi, void* lo, cudaStream_t stream);
+int mb200_maxpool2_nhwc_split(const void* xhi, const void* xlo, int B, int H, int W, int C, void* yhi, void* ylo,
+                              cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

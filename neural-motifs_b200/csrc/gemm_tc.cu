@@ -1,0 +1,360 @@
+// fp32-faithful tensor-core GEMM and 3x3 convolution for sm_100a: tcgen05.mma (kind::f16, bf16
+// operands, fp32 accumulation in TMEM) fed by TMA through an mbarrier ring.
+//
+// Precision scheme ("bf16x3"): every fp32 operand x is carried as a pair of bf16 tensors
+// (hi = bf16(x), lo = bf16(x - hi)); a product is accumulated as hi*hi + hi*lo + lo*hi in the
+// same TMEM accumulator.  That keeps ~16 mantissa bits per operand (relative error ~2^-16 per
+// product, fp32 accumulation), which is what the parity bar of the north star needs (fp32 logits
+// within 1e-3 of the reference's fp32 cuDNN/cuBLAS path through 15 stacked layers) — a single
+// bf16 or tf32 pass does not (DESIGN.md "precision").  Per k-block the kernel loads FOUR tiles
+// (A_hi, A_lo, B_hi, B_lo) and issues THREE MMAs per 16-wide k step.
+//
+// Replaces (a) cublasSgemm under nn.Linear: fc6/fc7 (lib/object_detector.py:102-103,129-138,
+// lib/rel_model.py:360-374), post_lstm / rel_compress (lib/rel_model.py:377,390), the hoisted LSTM
+// input projections; (b) cuDNN under nn.Conv2d for the 3x3/pad-1 VGG convolutions
+// (lib/object_detector.py:110-127) as an implicit GEMM whose A tiles are shifted TMA boxes of
+// the NHWC activation (out-of-bounds zero fill = the padding), no im2col buffer.
+//
+// Layout contract: A [M, Kp] and B [N, Kp] bf16, K contiguous ("K-major"), Kp % 64 == 0 with
+// zero padding; C row-major. Tile 128 x BN x 64, 128-byte swizzle, 3-stage ring (64 KB / stage),
+// warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2..5 = epilogue (one TMEM lane
+// quarter each).
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 64;
+constexpr int STAGES = 3;
+constexpr int TILE_A = BM * BK * 2;            // 16 KB
+constexpr int TILE_B = BN * BK * 2;            // 16 KB
+constexpr int STAGE_BYTES = 2 * TILE_A + 2 * TILE_B;
+constexpr int kGemmThreads = 192;
+constexpr int TMEM_COLS = 128;
+constexpr int TH = 8, TW = 16;                 // conv: spatial tile = 128 output pixels
+constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+
+struct Params {
+  int M, N;                  // logical output size (conv: M = B*H*W pixels, N = Cout)
+  int kblocks;               // k-blocks per split
+  int splits;
+  // epilogue targets (any may be null)
+  float* C; long long ldc;
+  __nv_bfloat16* Chi; __nv_bfloat16* Clo; long long ldsplit;
+  const float* bias; int relu;
+  float* partial;            // [splits][M][N] when splits > 1
+  // conv mode
+  int conv; int H, W, Cin, tiles_w, tiles_h;
+};
+
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant__ CUtensorMap tmAlo,
+                   const __grid_constant__ CUtensorMap tmBhi, const __grid_constant__ CUtensorMap tmBlo,
+                   const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = (uint64_t*)(smem + (size_t)STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = (uint32_t*)(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BN;
+  const int split = blockIdx.z;
+  const int kb0 = split * p.kblocks;
+
+  // tile origin
+  int m0 = 0, img = 0, h0 = 0, w0 = 0;
+  if (!p.conv) {
+    m0 = blockIdx.y * BM;
+  } else {
+    const int per_img = p.tiles_w * p.tiles_h;
+    img = blockIdx.y / per_img;
+    const int t = blockIdx.y - img * per_img;
+    h0 = (t / p.tiles_w) * TH;
+    w0 = (t - (t / p.tiles_w) * p.tiles_w) * TW;
+  }
+
+  if (warp == 0 && lane == 0) {
+    tc::prefetch_tmap(&tmAhi); tc::prefetch_tmap(&tmAlo); tc::prefetch_tmap(&tmBhi); tc::prefetch_tmap(&tmBlo);
+    for (int s = 0; s < STAGES; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
+    tc::mbar_init(tmem_full_bar, 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) tc::tmem_alloc(tmem_slot, TMEM_COLS);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------------------------------------------------------- TMA producer
+      int stage = 0; uint32_t phase = 0;
+      const int cblocks = p.conv ? p.Cin / BK : 0;
+      for (int kb = 0; kb < p.kblocks; ++kb) {
+        tc::mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* st = smem + (size_t)stage * STAGE_BYTES;
+        tc::mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+        const int kg = kb0 + kb;
+        if (!p.conv) {
+          tc::tma_load_2d(st, &tmAhi, &full_bar[stage], kg * BK, m0);
+          tc::tma_load_2d(st + TILE_A, &tmAlo, &full_bar[stage], kg * BK, m0);
+        } else {
+          const int tap = kg / cblocks, cb = kg - tap * cblocks;
+          const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
+          tc::tma_load_4d(st, &tmAhi, &full_bar[stage], cb * BK, w0 + dx, h0 + dy, img);
+          tc::tma_load_4d(st + TILE_A, &tmAlo, &full_bar[stage], cb * BK, w0 + dx, h0 + dy, img);
+        }
+        tc::tma_load_2d(st + 2 * TILE_A, &tmBhi, &full_bar[stage], kg * BK, n0);
+        tc::tma_load_2d(st + 2 * TILE_A + TILE_B, &tmBlo, &full_bar[stage], kg * BK, n0);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---------------------------------------------------------------- MMA issuer
+      constexpr uint32_t idesc = tc::umma_idesc_bf16_f32(BM, BN);
+      int stage = 0; uint32_t phase = 0;
+      for (int kb = 0; kb < p.kblocks; ++kb) {
+        tc::mbar_wait(&full_bar[stage], phase);
+        tc::tc_fence_after();
+        const uint32_t sa = tc::smem_u32(smem + (size_t)stage * STAGE_BYTES);
+        const uint64_t a_hi = tc::umma_desc_k_sw128(sa), a_lo = tc::umma_desc_k_sw128(sa + TILE_A);
+        const uint64_t b_hi = tc::umma_desc_k_sw128(sa + 2 * TILE_A), b_lo = tc::umma_desc_k_sw128(sa + 2 * TILE_A + TILE_B);
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          const uint64_t adv = (uint64_t)((k * 16 * 2) >> 4);   // 32 bytes per 16-wide k step
+          tc::umma_bf16(tmem_base, a_hi + adv, b_hi + adv, idesc, (kb | k) != 0);
+          tc::umma_bf16(tmem_base, a_hi + adv, b_lo + adv, idesc, 1);
+          tc::umma_bf16(tmem_base, a_lo + adv, b_hi + adv, idesc, 1);
+        }
+        tc::umma_commit(&empty_bar[stage]);          // frees the smem slot when these MMAs retire
+        if (kb == p.kblocks - 1) tc::umma_commit(tmem_full_bar);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    const int q = warp & 3;                    // TMEM lane quarter this warp may access
+    const int r = q * 32 + lane;               // tile row == TMEM lane
+    tc::mbar_wait(tmem_full_bar, 0);
+    tc::tc_fence_after();
+    long long row;                             // output row index (M axis), or -1 when masked
+    if (!p.conv) {
+      row = (m0 + r < p.M) ? (long long)(m0 + r) : -1;
+    } else {
+      const int h = h0 + r / TW, w = w0 + (r % TW);
+      row = (h < p.H && w < p.W) ? ((long long)img * p.H + h) * p.W + w : -1;
+    }
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      __syncwarp();                            // tcgen05.ld is warp-collective: reconverge first
+      uint32_t v[32];
+      tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+      tc::tmem_ld_wait();
+      const int nb = n0 + c * 32;
+      if (row < 0 || nb >= p.N) continue;
+      const int ncols = min(32, p.N - nb);
+      if (p.splits > 1) {
+        float* dst = p.partial + ((size_t)split * p.M + row) * p.N + nb;
+        for (int j = 0; j < ncols; ++j) dst[j] = __uint_as_float(v[j]);
+        continue;
+      }
+      float x[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float t = __uint_as_float(v[j]);
+        if (p.bias && j < ncols) t += __ldg(p.bias + nb + j);
+        if (p.relu) t = fmaxf(t, 0.f);
+        x[j] = t;
+      }
+      if (p.C) {
+        float* dst = p.C + row * p.ldc + nb;
+        if (ncols == 32 && ((((uintptr_t)dst) & 15) == 0)) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) ((float4*)dst)[j] = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+        } else {
+          for (int j = 0; j < ncols; ++j) dst[j] = x[j];
+        }
+      }
+      if (p.Chi) {
+        __align__(16) __nv_bfloat16 hi[32];
+        __align__(16) __nv_bfloat16 lo[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) tc::split_bf16(x[j], hi[j], lo[j]);
+        __nv_bfloat16* dh = p.Chi + row * p.ldsplit + nb;
+        __nv_bfloat16* dl = p.Clo + row * p.ldsplit + nb;
+        if (ncols == 32 && ((((uintptr_t)dh) & 15) == 0)) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { ((uint4*)dh)[j] = ((const uint4*)hi)[j]; ((uint4*)dl)[j] = ((const uint4*)lo)[j]; }
+        } else {
+          for (int j = 0; j < ncols; ++j) { dh[j] = hi[j]; dl[j] = lo[j]; }
+        }
+      }
+    }
+    tc::tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) { tc::tc_fence_after(); tc::tmem_dealloc(tmem_base, TMEM_COLS); }
+}
+
+// split-K second pass: out = sum_z partial[z] (+ bias) (relu) -> fp32 and/or split bf16
+__global__ void splitk_reduce_kernel(const float* __restrict__ partial, int splits, long long MN, int N,
+                                     const float* __restrict__ bias, int relu, float* __restrict__ C, long long ldc,
+                                     __nv_bfloat16* __restrict__ Chi, __nv_bfloat16* __restrict__ Clo, long long ldsplit) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < MN; i += (long long)blockDim.x * gridDim.x) {
+    float s = 0.f;
+    for (int z = 0; z < splits; ++z) s += partial[(size_t)z * MN + i];
+    const long long m = i / N; const int n = (int)(i - m * N);
+    if (bias) s += bias[n];
+    if (relu) s = fmaxf(s, 0.f);
+    if (C) C[m * ldc + n] = s;
+    if (Chi) { __nv_bfloat16 h, l; tc::split_bf16(s, h, l); Chi[m * ldsplit + n] = h; Clo[m * ldsplit + n] = l; }
+  }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult st;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &st) == cudaSuccess &&
+        st == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// 2D K-major bf16 matrix [rows, Kp] -> box {64, box_rows}, 128B swizzle, zero fill.
+bool make_tmap_2d(CUtensorMap* m, const void* ptr, long long rows, long long Kp, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)Kp, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)Kp * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// 4D NHWC bf16 activation [B,H,W,C] -> box {64, TW, TH, 1}
+bool make_tmap_nhwc(CUtensorMap* m, const void* ptr, int B, int H, int W, int C) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)TW, (cuuint32_t)TH, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+int ensure_attr() {
+  static bool done = false;
+  if (!done) {
+    MB200_CHECK(cudaFuncSetAttribute(gemm_bf16x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    done = true;
+  }
+  return MB200_OK;
+}
+
+int launch(const CUtensorMap& ahi, const CUtensorMap& alo, const CUtensorMap& bhi, const CUtensorMap& blo,
+           const Params& p, dim3 grid, cudaStream_t stream) {
+  int rc = ensure_attr();
+  if (rc != MB200_OK) return rc;
+  gemm_bf16x3_kernel<<<grid, kGemmThreads, SMEM_BYTES, stream>>>(ahi, alo, bhi, blo, p);
+  MB200_CHECK_LAUNCH("gemm_bf16x3_kernel");
+  if (p.splits > 1) {
+    const long long MN = (long long)p.M * p.N;
+    const int blocks = (int)min((long long)kNumSMs * 8, (MN + 255) / 256);
+    splitk_reduce_kernel<<<blocks, 256, 0, stream>>>(p.partial, p.splits, MN, p.N, p.bias, p.relu, p.C, p.ldc,
+                                                     p.Chi, p.Clo, p.ldsplit);
+    MB200_CHECK_LAUNCH("splitk_reduce_kernel");
+  }
+  return MB200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+// Floats of split-K workspace mb200_gemm_bf16x3 may need for an [M,N] output (0 when it will not split).
+long long mb200_gemm_workspace_floats(int M, int N, int Kp) {
+  const long long tiles = (long long)mb200_div_up(M, BM) * mb200_div_up(N, BN);
+  const int kblocks = Kp / BK;
+  if (tiles >= kNumSMs / 2 || kblocks < 8) return 0;
+  int splits = (int)min((long long)kblocks / 4, (long long)(kNumSMs / tiles));
+  if (splits < 2) return 0;
+  while (kblocks % splits) --splits;
+  return splits > 1 ? (long long)splits * M * N : 0;
+}
+
+// C[M,N] = A[M,K] * B[N,K]^T (+ bias[N]) (ReLU), A and B given as (hi, lo) bf16 pairs with row
+// pitch Kp (multiple of 64, zero padded). Outputs: C fp32 (ldc) and/or (Chi, Clo) bf16 pair
+// (ldsplit), any may be NULL. workspace: mb200_gemm_workspace_floats() floats or NULL.
+int mb200_gemm_bf16x3(const void* Ahi, const void* Alo, const void* Bhi, const void* Blo, int M, int N, int Kp,
+                      const float* bias, int relu, float* C, long long ldc, void* Chi, void* Clo,
+                      long long ldsplit, float* workspace, cudaStream_t stream) {
+  if (M <= 0 || N <= 0) return MB200_OK;
+  if (Kp <= 0 || Kp % BK != 0) return MB200_ERR_ARG;
+  CUtensorMap ta, tal, tb, tbl;
+  if (!make_tmap_2d(&ta, Ahi, M, Kp, BM) || !make_tmap_2d(&tal, Alo, M, Kp, BM) ||
+      !make_tmap_2d(&tb, Bhi, N, Kp, BN) || !make_tmap_2d(&tbl, Blo, N, Kp, BN)) {
+    mb200_set_error("cuTensorMapEncodeTiled", cudaErrorInvalidValue);
+    return MB200_ERR_CUDA;
+  }
+  Params p = {};
+  p.M = M; p.N = N;
+  const int kblocks = Kp / BK;
+  p.splits = 1;
+  if (workspace) {
+    const long long ws = mb200_gemm_workspace_floats(M, N, Kp);
+    if (ws > 0) p.splits = (int)(ws / ((long long)M * N));
+  }
+  p.kblocks = kblocks / p.splits;
+  p.C = C; p.ldc = ldc; p.Chi = (__nv_bfloat16*)Chi; p.Clo = (__nv_bfloat16*)Clo; p.ldsplit = ldsplit;
+  p.bias = bias; p.relu = relu; p.partial = workspace; p.conv = 0;
+  dim3 grid(mb200_div_up(N, BN), mb200_div_up(M, BM), p.splits);
+  if (grid.y > 65535) return MB200_ERR_UNSUPPORTED;
+  return launch(ta, tal, tb, tbl, p, grid, stream);
+}
+
+// 3x3 / stride 1 / pad 1 convolution as implicit GEMM. x: NHWC bf16 pair [B,H,W,Cin] (Cin % 64 == 0);
+// w: [Cout, 9*Cin] bf16 pair, K order (kh, kw, cin); outputs NHWC: y fp32 and/or (yhi, ylo), any NULL.
+int mb200_conv3x3_bf16x3(const void* xhi, const void* xlo, const void* whi, const void* wlo, int B, int H, int W,
+                         int Cin, int Cout, const float* bias, int relu, float* y, void* yhi, void* ylo,
+                         cudaStream_t stream) {
+  if (B <= 0 || H <= 0 || W <= 0 || Cout <= 0) return MB200_OK;
+  if (Cin % BK != 0) return MB200_ERR_ARG;
+  CUtensorMap ta, tal, tb, tbl;
+  const long long Kp = 9LL * Cin;
+  if (!make_tmap_nhwc(&ta, xhi, B, H, W, Cin) || !make_tmap_nhwc(&tal, xlo, B, H, W, Cin) ||
+      !make_tmap_2d(&tb, whi, Cout, Kp, BN) || !make_tmap_2d(&tbl, wlo, Cout, Kp, BN)) {
+    mb200_set_error("cuTensorMapEncodeTiled", cudaErrorInvalidValue);
+    return MB200_ERR_CUDA;
+  }
+  Params p = {};
+  p.M = B * H * W; p.N = Cout; p.splits = 1; p.kblocks = (int)(Kp / BK);
+  p.C = y; p.ldc = Cout; p.Chi = (__nv_bfloat16*)yhi; p.Clo = (__nv_bfloat16*)ylo; p.ldsplit = Cout;
+  p.bias = bias; p.relu = relu; p.partial = nullptr;
+  p.conv = 1; p.H = H; p.W = W; p.Cin = Cin; p.tiles_w = mb200_div_up(W, TW); p.tiles_h = mb200_div_up(H, TH);
+  const long long tiles = (long long)B * p.tiles_w * p.tiles_h;
+  if (tiles > 65535) {
+    // grid.y limit: fold tiles into x (n-tiles stay fastest so that B tiles of a pixel tile share A in L2)
+    return MB200_ERR_UNSUPPORTED;
+  }
+  dim3 grid(mb200_div_up(Cout, BN), (unsigned)tiles, 1);
+  return launch(ta, tal, tb, tbl, p, grid, stream);
+}
+
+}  // extern "C"

@@ -83,6 +83,7 @@ nms_reduce_kernel(const unsigned long long* __restrict__ mask, const int* __rest
   __shared__ unsigned long long s_keepmask;   // kept boxes of the current chunk
   __shared__ unsigned long long s_remv_cur;   // remv word of the current chunk
   __shared__ int s_count;
+  __shared__ int s_rows[kTile];
   unsigned long long remv[kMaxWordsPerThread];
 #pragma unroll
   for (int k = 0; k < kMaxWordsPerThread; ++k) remv[k] = 0ULL;
@@ -123,18 +124,28 @@ nms_reduce_kernel(const unsigned long long* __restrict__ mask, const int* __rest
     __syncthreads();
     const unsigned long long kept = s_keepmask;
     if (kept) {
-      // OR rows of kept boxes into the words this thread owns (only words > chunk matter)
+      // OR the rows of the kept boxes into the words this thread owns (only words > chunk
+      // matter). Loads are issued 8 at a time so their L2 latencies overlap.
+      const int nk = __popcll(kept);
+      if (threadIdx.x < 64) {   // compact list of kept rows of this chunk
+        const unsigned long long below = kept & ((1ULL << threadIdx.x) - 1ULL);
+        if (kept & (1ULL << threadIdx.x)) s_rows[__popcll(below)] = chunk * kTile + threadIdx.x;
+      }
+      __syncthreads();
 #pragma unroll
       for (int k = 0; k < kMaxWordsPerThread; ++k) {
         const int w = threadIdx.x + k * kReduceThreads;
         if (w > chunk && w < col_blocks) {
           unsigned long long acc = remv[k];
-          unsigned long long kk = kept;
-          while (kk) {
-            const int i = __ffsll((long long)kk) - 1;
-            kk &= kk - 1;
-            acc |= m[(long long)(chunk * kTile + i) * col_blocks + w];
+          int i = 0;
+          for (; i + 8 <= nk; i += 8) {
+            unsigned long long v[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[q] = m[(long long)s_rows[i + q] * col_blocks + w];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) acc |= v[q];
           }
+          for (; i < nk; ++i) acc |= m[(long long)s_rows[i] * col_blocks + w];
           remv[k] = acc;
         }
       }

@@ -7,12 +7,16 @@
 // outside the image, rois whose batch index is out of range produce zeros.
 //
 // Design (HBM-bound op; see DESIGN.md "RoIAlign"):
-//   * one CTA per (roi, 32-channel chunk); the per-roi sample table (4 offsets + 2 lerp
-//     weights per bin) is computed once into shared memory instead of once per element
-//     with integer div/mod as the reference does;
-//   * the roi's window of the feature plane is staged in shared memory (small boxes
-//     re-read every pixel ~3x), then every output is produced from shared memory;
-//   * outputs are written bin-fastest so a warp stores one contiguous 128 B line.
+//   * one CTA per (roi, 64-channel chunk); the per-roi sample table (4 window offsets + 2 lerp
+//     weights per bin) is computed once by one warp instead of once per element with integer
+//     div/mod as the reference does;
+//   * NCHW: the roi's window of each feature plane is staged in shared memory transposed to
+//     [pixel][channel] (row stride 33 words), so that in the compute phase the 32 lanes of a
+//     warp are 32 channels of ONE bin: every shared-memory read is conflict-free and the bin's
+//     table entry is a broadcast; results go through a [channel][bin] tile and leave as
+//     contiguous 16-byte vector stores (the output of a chunk is one contiguous run);
+//   * NHWC: lanes are channel quads, loads and stores are 16-byte vectors straight from L2;
+//   * windows larger than 256 px (bins >= 1 px apart, no re-use to exploit) gather from global.
 #include "common.cuh"
 
 namespace {
@@ -20,9 +24,7 @@ namespace {
 constexpr int kMaxCrop = 32;     // fast kernels: crop_h, crop_w <= 32 and crop_h*crop_w <= 256
 constexpr int kMaxBins = 256;
 constexpr int kThreads = 256;
-constexpr int kChunk   = 32;     // channels per CTA
-constexpr int kWinFloats = 8192; // 32 KB dynamic shared memory for the staged window
-constexpr int kStageMaxArea = kWinFloats / kChunk;  // 256 px: one pass covers the whole chunk
+constexpr int kChunk   = 32;     // channels per CTA (backward kernel)
 
 struct BinTab {
   int   o00[kMaxBins], o01[kMaxBins], o10[kMaxBins], o11[kMaxBins];
@@ -85,88 +87,220 @@ __device__ __forceinline__ void build_tables(const float* __restrict__ boxes, in
 }
 
 // ---------------------------------------------------------------- forward, NCHW -> [N,C,PH,PW]
+constexpr int kLanes = 32;               // channels per pass == warp width
+constexpr int kPasses = 2;               // passes per CTA -> 64 channels per CTA
+constexpr int kWinStride = kLanes + 1;   // [pixel][channel] rows padded to 33 words
+constexpr int kStageMaxArea = 256;       // windows up to 16x16 px are staged
+
+struct __align__(16) BinDesc { int o00, o01, o10, o11; };   // window pixel indices of the 4 corners
+struct __align__(8) BinW { float wx, wy; };
+
+// Warp 0 builds the axis tables and the window; everyone then derives bin descriptors.
+struct RoiHead { int b_in, y_lo, x_lo, wh, ww, any_ok, bad_batch; };
+
+__device__ __forceinline__ void roi_preamble(const float* __restrict__ boxes, int n, int batch, int H, int W,
+                                             int PH, int PW, AxisTab& ty, AxisTab& tx, RoiHead& hd) {
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    const float* bx = boxes + (size_t)n * 5;
+    const int b_in = (int)bx[0];
+    const float x1 = bx[1], y1 = bx[2], x2 = bx[3], y2 = bx[4];
+    int ylo = H, yhi = -1, xlo = W, xhi = -1;
+    if (lane < PH) {
+      int lo, hi, ok; float lerp;
+      axis_sample(y1, y2, H, PH, lane, &lo, &hi, &lerp, &ok);
+      ty.lo[lane] = lo; ty.hi[lane] = hi; ty.lerp[lane] = lerp; ty.ok[lane] = ok;
+      if (ok) { ylo = lo; yhi = hi; }
+    }
+    if (lane < PW) {
+      int lo, hi, ok; float lerp;
+      axis_sample(x1, x2, W, PW, lane, &lo, &hi, &lerp, &ok);
+      tx.lo[lane] = lo; tx.hi[lane] = hi; tx.lerp[lane] = lerp; tx.ok[lane] = ok;
+      if (ok) { xlo = lo; xhi = hi; }
+    }
+    ylo = __reduce_min_sync(0xffffffffu, ylo); yhi = __reduce_max_sync(0xffffffffu, yhi);
+    xlo = __reduce_min_sync(0xffffffffu, xlo); xhi = __reduce_max_sync(0xffffffffu, xhi);
+    if (lane == 0) {
+      hd.b_in = b_in;
+      hd.bad_batch = (b_in < 0 || b_in >= batch);
+      hd.any_ok = (yhi >= 0 && xhi >= 0 && !hd.bad_batch);
+      hd.y_lo = ylo; hd.x_lo = xlo; hd.wh = yhi - ylo + 1; hd.ww = xhi - xlo + 1;
+    }
+  }
+  __syncthreads();
+}
+
 __global__ void __launch_bounds__(kThreads)
 roi_align_fwd_nchw_kernel(const float* __restrict__ feat, const float* __restrict__ boxes,
                           int num_boxes, int batch, int H, int W, int PH, int PW, int C,
                           float extrap, float* __restrict__ out) {
-  extern __shared__ float s_win[];
+  extern __shared__ __align__(16) float dsm[];
   __shared__ AxisTab ty, tx;
-  __shared__ BinTab tb;
-  __shared__ RoiInfo info;
+  __shared__ RoiHead hd;
+  __shared__ BinDesc s_desc[kMaxBins];
+  __shared__ BinW s_w[kMaxBins];
+  __shared__ int s_ok[kMaxBins];
+  __shared__ int s_goff[kStageMaxArea];
+  const int bins = PH * PW;
+  float* s_out = dsm;                        // [32][bins]
+  float* s_win = dsm + kLanes * bins;        // [area][33]
 
   const int n = blockIdx.x;
-  const int c0 = blockIdx.y * kChunk;
-  const int nc = min(kChunk, C - c0);
-  const int tid = threadIdx.x;
-  const int bins = PH * PW;
+  const int cbase = blockIdx.y * (kLanes * kPasses);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int kWarps = kThreads / 32;
 
-  build_tables(boxes, n, batch, H, W, PH, PW, ty, tx, info);
+  roi_preamble(boxes, n, batch, H, W, PH, PW, ty, tx, hd);
 
-  float* o = out + ((size_t)n * C + c0) * bins;
-  const int total = nc * bins;
-  if (!info.any_ok) {
-    // roi outside the batch -> zeros (the reference leaves the caller's zero fill untouched);
-    // every sample outside the image -> extrapolation value.
-    const bool bad_batch = (info.b_in < 0 || info.b_in >= batch);
-    const float v = bad_batch ? 0.f : extrap;
-    for (int i = tid; i < total; i += kThreads) o[i] = v;
+  const int nc_cta = min(kLanes * kPasses, C - cbase);
+  float* o_cta = out + ((size_t)n * C + cbase) * bins;
+  if (!hd.any_ok) {
+    const float v = hd.bad_batch ? 0.f : extrap;
+    for (int i = tid; i < nc_cta * bins; i += kThreads) o_cta[i] = v;
     return;
   }
-
-  const int area = info.wh * info.ww;
+  const int area = hd.wh * hd.ww;
   const bool staged = area <= kStageMaxArea;
-  const int ww = info.ww;
+  const int ww = hd.ww;
   for (int b = tid; b < bins; b += kThreads) {
     const int y = b / PW, x = b - y * PW;
     const int ok = ty.ok[y] & tx.ok[x];
-    tb.ok[b] = ok;
-    tb.wx[b] = tx.lerp[x];
-    tb.wy[b] = ty.lerp[y];
+    s_ok[b] = ok;
+    BinW w; w.wx = tx.lerp[x]; w.wy = ty.lerp[y]; s_w[b] = w;
+    BinDesc d;
     if (staged) {
-      const int yt = ty.lo[y] - info.y_lo, yb = ty.hi[y] - info.y_lo;
-      const int xl = tx.lo[x] - info.x_lo, xr = tx.hi[x] - info.x_lo;
-      tb.o00[b] = ok ? yt * ww + xl : 0; tb.o01[b] = ok ? yt * ww + xr : 0;
-      tb.o10[b] = ok ? yb * ww + xl : 0; tb.o11[b] = ok ? yb * ww + xr : 0;
+      const int yt = ty.lo[y] - hd.y_lo, yb = ty.hi[y] - hd.y_lo;
+      const int xl = tx.lo[x] - hd.x_lo, xr = tx.hi[x] - hd.x_lo;
+      d.o00 = ok ? (yt * ww + xl) * kWinStride : 0; d.o01 = ok ? (yt * ww + xr) * kWinStride : 0;
+      d.o10 = ok ? (yb * ww + xl) * kWinStride : 0; d.o11 = ok ? (yb * ww + xr) * kWinStride : 0;
     } else {
-      tb.o00[b] = ty.lo[y] * W + tx.lo[x]; tb.o01[b] = ty.lo[y] * W + tx.hi[x];
-      tb.o10[b] = ty.hi[y] * W + tx.lo[x]; tb.o11[b] = ty.hi[y] * W + tx.hi[x];
+      d.o00 = ty.lo[y] * W + tx.lo[x]; d.o01 = ty.lo[y] * W + tx.hi[x];
+      d.o10 = ty.hi[y] * W + tx.lo[x]; d.o11 = ty.hi[y] * W + tx.hi[x];
     }
+    s_desc[b] = d;
   }
+  if (staged)
+    for (int r = tid; r < area; r += kThreads) {
+      const int wy_ = r / ww, wx_ = r - wy_ * ww;
+      s_goff[r] = (hd.y_lo + wy_) * W + hd.x_lo + wx_;
+    }
+  __syncthreads();
 
-  const float* plane0 = feat + ((size_t)info.b_in * C + c0) * H * W;
-  if (staged) {
-    // Stage the window of every channel of the chunk: s_win[c][r], r = wy*ww + wx.
-    __syncthreads();
-    const size_t base = (size_t)info.y_lo * W + info.x_lo;
-    // Each warp walks channels; lanes walk window elements.
-    const int warp = tid >> 5, lane = tid & 31, nwarps = kThreads >> 5;
-    for (int c = warp; c < nc; c += nwarps) {
-      const float* p = plane0 + (size_t)c * H * W + base;
-      float* d = s_win + c * area;
-      for (int r = lane; r < area; r += 32) {
-        const int wy_ = r / ww, wx_ = r - wy_ * ww;
-        d[r] = __ldg(p + wy_ * W + wx_);
+  const size_t HW = (size_t)H * W;
+  const bool vec_ok = (((size_t)C * bins) % 4 == 0) && ((((uintptr_t)out) & 15) == 0) && ((kLanes * bins) % 4 == 0);
+  for (int pass = 0; pass < kPasses; ++pass) {
+    const int c0 = cbase + pass * kLanes;
+    const int nc = min(kLanes, C - c0);
+    if (nc <= 0) break;
+    const float* plane0 = feat + ((size_t)hd.b_in * C + c0) * HW;
+    float* o = out + ((size_t)n * C + c0) * bins;
+    if (staged) {
+      // stage: warp -> channel, lanes -> window pixels; transposed store, stride 33: conflict-free
+      for (int c = warp; c < nc; c += kWarps) {
+        const float* p = plane0 + (size_t)c * HW;
+        for (int r = lane; r < area; r += 32) s_win[r * kWinStride + c] = __ldg(p + s_goff[r]);
+      }
+      __syncthreads();
+      // compute: warp -> bin, lanes -> channels
+      const float* wl = s_win + lane;
+      for (int b = warp; b < bins; b += kWarps) {
+        const BinDesc d = s_desc[b];
+        const BinW w = s_w[b];
+        float v = extrap;
+        if (s_ok[b]) v = bilerp(wl[d.o00], wl[d.o01], wl[d.o10], wl[d.o11], w.wx, w.wy);
+        s_out[lane * bins + b] = v;
+      }
+      __syncthreads();
+      // store: the chunk's output is one contiguous run of nc*bins floats
+      const int total = nc * bins;
+      if (vec_ok) {
+        const float4* src = (const float4*)s_out;
+        float4* dst = (float4*)o;
+        for (int i = tid; i < total / 4; i += kThreads) dst[i] = src[i];
+      } else {
+        for (int i = tid; i < total; i += kThreads) o[i] = s_out[i];
+      }
+      __syncthreads();
+    } else {
+      const int total = nc * bins;
+      for (int i = tid; i < total; i += kThreads) {
+        const int c = i / bins, b = i - c * bins;
+        const float* p = plane0 + (size_t)c * HW;
+        const BinDesc d = s_desc[b];
+        const BinW w = s_w[b];
+        float v = extrap;
+        if (s_ok[b]) v = bilerp(__ldg(p + d.o00), __ldg(p + d.o01), __ldg(p + d.o10), __ldg(p + d.o11), w.wx, w.wy);
+        o[i] = v;
       }
     }
-    __syncthreads();
-    for (int i = tid; i < total; i += kThreads) {
-      const int c = i / bins, b = i - c * bins;
-      const float* d = s_win + c * area;
-      float v = extrap;
-      if (tb.ok[b]) v = bilerp(d[tb.o00[b]], d[tb.o01[b]], d[tb.o10[b]], d[tb.o11[b]], tb.wx[b], tb.wy[b]);
-      o[i] = v;
+  }
+}
+
+// ---------------------------------------------------------------- forward, NHWC -> [N, PH*PW, C]
+// Pipeline variant: the backbone epilogue leaves conv5_3 as NHWC fp32; pooled features come out
+// bin-major / channel-minor, the K order the fc6 tensor-core GEMM consumes. One CTA per
+// (roi, 128-channel chunk): a warp owns one bin at a time, each lane 4 consecutive channels.
+constexpr int kChunkNHWC = 128;
+__global__ void __launch_bounds__(kThreads)
+roi_align_fwd_nhwc_kernel(const float* __restrict__ feat, const float* __restrict__ boxes,
+                          int num_boxes, int batch, int H, int W, int PH, int PW, int C,
+                          float extrap, float* __restrict__ out) {
+  __shared__ AxisTab ty, tx;
+  __shared__ RoiHead hd;
+  const int n = blockIdx.x;
+  const int c0 = blockIdx.y * kChunkNHWC;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int kWarps = kThreads / 32;
+  const int bins = PH * PW;
+  roi_preamble(boxes, n, batch, H, W, PH, PW, ty, tx, hd);
+  const int c = c0 + 4 * lane;
+  if (c >= C) return;
+  float* o = out + (size_t)n * bins * C + c;
+  const float* img = feat + (size_t)(hd.bad_batch ? 0 : hd.b_in) * H * W * C + c;
+  for (int b = warp; b < bins; b += kWarps) {
+    const int y = b / PW, x = b - y * PW;
+    float4 v;
+    if (hd.bad_batch) v = make_float4(0.f, 0.f, 0.f, 0.f);
+    else if (!(ty.ok[y] & tx.ok[x])) v = make_float4(extrap, extrap, extrap, extrap);
+    else {
+      const float* r0 = img + (size_t)(ty.lo[y] * W) * C;
+      const float* r1 = img + (size_t)(ty.hi[y] * W) * C;
+      const size_t xl = (size_t)tx.lo[x] * C, xr = (size_t)tx.hi[x] * C;
+      const float4 tl = __ldg((const float4*)(r0 + xl)), tr = __ldg((const float4*)(r0 + xr));
+      const float4 bl = __ldg((const float4*)(r1 + xl)), br = __ldg((const float4*)(r1 + xr));
+      const float wx = tx.lerp[x], wy = ty.lerp[y];
+      v.x = bilerp(tl.x, tr.x, bl.x, br.x, wx, wy); v.y = bilerp(tl.y, tr.y, bl.y, br.y, wx, wy);
+      v.z = bilerp(tl.z, tr.z, bl.z, br.z, wx, wy); v.w = bilerp(tl.w, tr.w, bl.w, br.w, wx, wy);
     }
-  } else {
-    __syncthreads();
-    for (int i = tid; i < total; i += kThreads) {
-      const int c = i / bins, b = i - c * bins;
-      const float* p = plane0 + (size_t)c * H * W;
-      float v = extrap;
-      if (tb.ok[b])
-        v = bilerp(__ldg(p + tb.o00[b]), __ldg(p + tb.o01[b]), __ldg(p + tb.o10[b]), __ldg(p + tb.o11[b]),
-                   tb.wx[b], tb.wy[b]);
-      o[i] = v;
+    *(float4*)(o + (size_t)b * C) = v;
+  }
+}
+
+// scalar NHWC fallback for channel counts that are not a multiple of 4
+__global__ void __launch_bounds__(kThreads)
+roi_align_fwd_nhwc_scalar_kernel(const float* __restrict__ feat, const float* __restrict__ boxes,
+                                 int num_boxes, int batch, int H, int W, int PH, int PW, int C,
+                                 float extrap, float* __restrict__ out) {
+  __shared__ AxisTab ty, tx;
+  __shared__ RoiHead hd;
+  const int n = blockIdx.x;
+  const int bins = PH * PW;
+  roi_preamble(boxes, n, batch, H, W, PH, PW, ty, tx, hd);
+  float* o = out + (size_t)n * bins * C;
+  const float* img = feat + (size_t)(hd.bad_batch ? 0 : hd.b_in) * H * W * C;
+  for (int i = threadIdx.x; i < bins * C; i += kThreads) {
+    const int b = i / C, c = i - b * C;
+    const int y = b / PW, x = b - y * PW;
+    float v;
+    if (hd.bad_batch) v = 0.f;
+    else if (!(ty.ok[y] & tx.ok[x])) v = extrap;
+    else {
+      const float* r0 = img + (size_t)(ty.lo[y] * W) * C + c;
+      const float* r1 = img + (size_t)(ty.hi[y] * W) * C + c;
+      v = bilerp(__ldg(r0 + (size_t)tx.lo[x] * C), __ldg(r0 + (size_t)tx.hi[x] * C),
+                 __ldg(r1 + (size_t)tx.lo[x] * C), __ldg(r1 + (size_t)tx.hi[x] * C), tx.lerp[x], ty.lerp[y]);
     }
+    o[i] = v;
   }
 }
 
@@ -265,46 +399,6 @@ __global__ void roi_align_bwd_generic_kernel(const long long nthreads, const flo
   }
 }
 
-// ---------------------------------------------------------------- forward, NHWC -> [N, PH*PW, C]
-// Pipeline variant: the backbone epilogue leaves conv5_3 as NHWC fp32; pooled features
-// come out bin-major / channel-minor ("channels last"), which is the K order the fc6
-// tensor-core GEMM consumes.  One CTA per (roi, 64-channel chunk).
-constexpr int kChunkNHWC = 64;
-__global__ void __launch_bounds__(kThreads)
-roi_align_fwd_nhwc_kernel(const float* __restrict__ feat, const float* __restrict__ boxes,
-                          int num_boxes, int batch, int H, int W, int PH, int PW, int C,
-                          float extrap, float* __restrict__ out) {
-  __shared__ AxisTab ty, tx;
-  __shared__ RoiInfo info;
-  const int n = blockIdx.x;
-  const int c0 = blockIdx.y * kChunkNHWC;
-  const int nc = min(kChunkNHWC, C - c0);
-  const int tid = threadIdx.x;
-  const int bins = PH * PW;
-  build_tables(boxes, n, batch, H, W, PH, PW, ty, tx, info);
-  float* o = out + (size_t)n * bins * C + c0;
-  const bool bad_batch = (info.b_in < 0 || info.b_in >= batch);
-  const float* img = feat + (size_t)(bad_batch ? 0 : info.b_in) * H * W * C + c0;
-  // thread -> (bin group, channel): channel fastest so loads and stores are coalesced.
-  const int cl = tid % kChunkNHWC;
-  const int bg = tid / kChunkNHWC;               // 0..3
-  const int bstep = kThreads / kChunkNHWC;
-  if (cl >= nc) return;
-  for (int b = bg; b < bins; b += bstep) {
-    const int y = b / PW, x = b - y * PW;
-    float v;
-    if (bad_batch) v = 0.f;
-    else if (!(ty.ok[y] & tx.ok[x])) v = extrap;
-    else {
-      const float* r0 = img + (size_t)(ty.lo[y] * W) * C;
-      const float* r1 = img + (size_t)(ty.hi[y] * W) * C;
-      const int xl = tx.lo[x] * C + cl, xr = tx.hi[x] * C + cl;
-      v = bilerp(__ldg(r0 + xl), __ldg(r0 + xr), __ldg(r1 + xl), __ldg(r1 + xr), tx.lerp[x], ty.lerp[y]);
-    }
-    o[(size_t)b * C + cl] = v;
-  }
-}
-
 }  // namespace
 
 extern "C" {
@@ -316,10 +410,17 @@ int ROIAlignForwardLaucher(const float* image_ptr, const float* boxes_ptr, int n
   if (num_boxes <= 0 || depth <= 0) return MB200_OK;
   if (crop_height <= 0 || crop_width <= 0 || image_height <= 0 || image_width <= 0) return MB200_ERR_ARG;
   const int bins = crop_height * crop_width;
-  const int chunks = mb200_div_up(depth, kChunk);
+  const int chunks = mb200_div_up(depth, kLanes * kPasses);
   if (crop_height <= kMaxCrop && crop_width <= kMaxCrop && bins <= kMaxBins && chunks <= 65535) {
     dim3 grid(num_boxes, chunks);
-    roi_align_fwd_nchw_kernel<<<grid, kThreads, kWinFloats * sizeof(float), stream>>>(
+    const size_t smem = ((size_t)kLanes * bins + (size_t)kStageMaxArea * kWinStride) * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+      MB200_CHECK(cudaFuncSetAttribute(roi_align_fwd_nchw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)(((size_t)kLanes * kMaxBins + (size_t)kStageMaxArea * kWinStride) * sizeof(float))));
+      attr_set = true;
+    }
+    roi_align_fwd_nchw_kernel<<<grid, kThreads, smem, stream>>>(
         image_ptr, boxes_ptr, num_boxes, batch, image_height, image_width, crop_height, crop_width,
         depth, extrapolation_value, crops_ptr);
   } else {
@@ -363,9 +464,14 @@ int mb200_roi_align_forward_nhwc(const float* image_nhwc, const float* boxes_ptr
   if (num_boxes <= 0 || depth <= 0) return MB200_OK;
   if (crop_height <= 0 || crop_width <= 0 || crop_height > kMaxCrop || crop_width > kMaxCrop)
     return MB200_ERR_ARG;
-  dim3 grid(num_boxes, mb200_div_up(depth, kChunkNHWC));
-  roi_align_fwd_nhwc_kernel<<<grid, kThreads, 0, stream>>>(image_nhwc, boxes_ptr, num_boxes, batch,
-      image_height, image_width, crop_height, crop_width, depth, extrapolation_value, crops_nhwc);
+  if (depth % 4 == 0 && ((((uintptr_t)image_nhwc) | ((uintptr_t)crops_nhwc)) & 15) == 0) {
+    dim3 grid(num_boxes, mb200_div_up(depth, kChunkNHWC));
+    roi_align_fwd_nhwc_kernel<<<grid, kThreads, 0, stream>>>(image_nhwc, boxes_ptr, num_boxes, batch,
+        image_height, image_width, crop_height, crop_width, depth, extrapolation_value, crops_nhwc);
+  } else {
+    roi_align_fwd_nhwc_scalar_kernel<<<num_boxes, kThreads, 0, stream>>>(image_nhwc, boxes_ptr, num_boxes, batch,
+        image_height, image_width, crop_height, crop_width, depth, extrapolation_value, crops_nhwc);
+  }
   MB200_CHECK_LAUNCH("mb200_roi_align_forward_nhwc");
   return MB200_OK;
 }

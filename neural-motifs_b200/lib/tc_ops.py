@@ -1,0 +1,231 @@
+"""Host side of the bf16x3 tensor-core path (csrc/gemm_tc.cu): operand splitting with a
+per-parameter cache, `linear_tc` (drop-in for F.linear with autograd) and the VGG feature
+extractor built from the implicit-GEMM 3x3 convolution.
+
+The arithmetic replaced is nn.Linear / nn.Conv2d of the reference (cuBLAS / cuDNN fp32):
+fc6/fc7 `lib/object_detector.py:129-138`, `lib/rel_model.py:360-374,439-448`, post_lstm /
+rel_compress `lib/rel_model.py:377,390,503,524`, VGG16 features `lib/object_detector.py:110-127`.
+"""
+import torch
+from torch.autograd import Function
+
+import motifs_cabi as _c
+
+
+def _round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+class SplitMat(object):
+    """(hi, lo) bf16 pair of a logical [rows, K] fp32 matrix, row pitch Kp (multiple of 64)."""
+    __slots__ = ("hi", "lo", "rows", "K", "Kp")
+
+    def __init__(self, hi, lo, rows, K, Kp):
+        self.hi, self.lo, self.rows, self.K, self.Kp = hi, lo, rows, K, Kp
+
+
+def split_rows(x):
+    """x [R,K] fp32 CUDA (row stride arbitrary, unit column stride) -> SplitMat of x."""
+    _c.require_cuda(x)
+    assert x.dim() == 2 and x.dtype == torch.float32
+    if x.stride(1) != 1:
+        x = x.contiguous()
+    R, K = x.shape
+    Kp = _round_up(K, 64)
+    hi = torch.empty(R, Kp, dtype=torch.bfloat16, device=x.device)
+    lo = torch.empty(R, Kp, dtype=torch.bfloat16, device=x.device)
+    with torch.cuda.device(x.device):
+        _c.check(_c.load().mb200_split_bf16(_c.ptr(x), R, K, x.stride(0), Kp, _c.ptr(hi), _c.ptr(lo), _c.cur_stream()),
+                 "mb200_split_bf16")
+    return SplitMat(hi, lo, R, K, Kp)
+
+
+def split_transposed(x):
+    """x [R,C] fp32 CUDA -> SplitMat of x^T: logical [C, R], pitch round_up(R, 64)."""
+    _c.require_cuda(x)
+    assert x.dim() == 2 and x.dtype == torch.float32
+    if x.stride(1) != 1:
+        x = x.contiguous()
+    R, Cc = x.shape
+    Rp = _round_up(R, 64)
+    hi = torch.empty(Cc, Rp, dtype=torch.bfloat16, device=x.device)
+    lo = torch.empty(Cc, Rp, dtype=torch.bfloat16, device=x.device)
+    with torch.cuda.device(x.device):
+        _c.check(_c.load().mb200_split_transpose_bf16(_c.ptr(x), R, Cc, x.stride(0), Rp, _c.ptr(hi), _c.ptr(lo),
+                                                      _c.cur_stream()), "mb200_split_transpose_bf16")
+    return SplitMat(hi, lo, Cc, R, Rp)
+
+
+def gemm(A, B, bias=None, relu=False, want_f32=True, want_split=False):
+    """C = A @ B^T (+bias)(relu) with A [M,K], B [N,K] SplitMats. Returns fp32 [M,N] and/or a SplitMat
+    of C (pitch round_up(N,64), zero padded) per the flags."""
+    assert A.Kp == B.Kp, (A.Kp, B.Kp)
+    M, N = A.rows, B.rows
+    dev = A.hi.device
+    C = torch.empty(M, N, dtype=torch.float32, device=dev) if want_f32 else None
+    Cs = None
+    if want_split:
+        Np = _round_up(N, 64)
+        alloc = torch.zeros if Np != N else torch.empty
+        Cs = SplitMat(alloc(M, Np, dtype=torch.bfloat16, device=dev), alloc(M, Np, dtype=torch.bfloat16, device=dev),
+                      M, N, Np)
+    lib = _c.load()
+    ws_n = lib.mb200_gemm_workspace_floats(M, N, A.Kp)
+    ws = torch.empty(ws_n, dtype=torch.float32, device=dev) if ws_n > 0 else None
+    with torch.cuda.device(dev):
+        rc = lib.mb200_gemm_bf16x3(_c.ptr(A.hi), _c.ptr(A.lo), _c.ptr(B.hi), _c.ptr(B.lo), M, N, A.Kp,
+                                   _c.ptr(bias), 1 if relu else 0, _c.ptr(C), N,
+                                   _c.ptr(Cs.hi) if Cs else None, _c.ptr(Cs.lo) if Cs else None,
+                                   Cs.Kp if Cs else 0, _c.ptr(ws), _c.cur_stream())
+    _c.check(rc, "mb200_gemm_bf16x3")
+    if want_f32 and want_split:
+        return C, Cs
+    return C if want_f32 else Cs
+
+
+# ------------------------------------------------------------------ weight split cache
+_cache = {}
+
+
+def _cached(param, kind, maker):
+    """Split copies of a parameter are rebuilt only when the parameter changes (optimizer steps
+    bump `_version`); frozen weights are split once."""
+    key = (id(param), kind)
+    ver = (param.data_ptr(), param._version, tuple(param.shape))
+    hit = _cache.get(key)
+    if hit is not None and hit[0] == ver:
+        return hit[1]
+    val = maker(param.detach())
+    _cache[key] = (ver, val)
+    return val
+
+
+def weight_split(weight):          # [N,K] -> B operand of  x @ W^T
+    return _cached(weight, "rows", split_rows)
+
+
+def weight_split_t(weight):        # [N,K] -> W^T as [K,N]: B operand of  dY @ W
+    return _cached(weight, "cols", split_transposed)
+
+
+def clear_cache():
+    _cache.clear()
+
+
+class _LinearTC(Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        xs = split_rows(x.detach())
+        y = gemm(xs, weight_split(weight), bias=bias.detach() if bias is not None else None)
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, weight = ctx.saved_tensors
+        gy = gy.contiguous()
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = gemm(split_rows(gy), weight_split_t(weight))                 # [M,N] x [K,N]^T -> [M,K]
+        if ctx.needs_input_grad[1]:
+            gw = gemm(split_transposed(gy), split_transposed(x.detach()))     # [N,M] x [K,M]^T -> [N,K]
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = gy.sum(0)
+        return gx, gw, gb
+
+
+def linear_tc(x, weight, bias=None):
+    """F.linear(x, weight, bias) on the tcgen05 path (fp32 in / fp32 out, autograd aware)."""
+    _c.require_cuda(x, weight)
+    shp = x.shape
+    y = _LinearTC.apply(x.reshape(-1, shp[-1]), weight, bias)
+    return y.reshape(*shp[:-1], weight.size(0))
+
+
+def linear_tc_nograd(x_split, weight, bias=None, relu=False, want_f32=True, want_split=False):
+    """Inference-side linear on an already split input; ReLU fused; may emit the split output so
+    that chained layers (fc6 -> fc7) never materialise fp32 activations."""
+    return gemm(x_split, weight_split(weight), bias=bias, relu=relu, want_f32=want_f32, want_split=want_split)
+
+
+# ------------------------------------------------------------------ VGG16 features (frozen, forward only)
+VGG16_CFG = [64, 64, 'M', 128, 128, 'M', 256, 256, 256, 'M', 512, 512, 512, 'M', 512, 512, 512]
+
+
+def _conv_weight_split(conv_weight):
+    def mk(w):
+        O, I = w.size(0), w.size(1)
+        dev = w.device
+        lib = _c.load()
+        w = w.contiguous()
+        if I == 3:
+            hi = torch.empty(O, 64, dtype=torch.bfloat16, device=dev); lo = torch.empty_like(hi)
+            with torch.cuda.device(dev):
+                _c.check(lib.mb200_stem_weight_split(_c.ptr(w), O, _c.ptr(hi), _c.ptr(lo), _c.cur_stream()), "stem_weight")
+            return SplitMat(hi, lo, O, 27, 64)
+        Ip = _round_up(I, 64)
+        hi = torch.empty(O, 9 * Ip, dtype=torch.bfloat16, device=dev); lo = torch.empty_like(hi)
+        with torch.cuda.device(dev):
+            _c.check(lib.mb200_conv_weight_split(_c.ptr(w), O, I, Ip, _c.ptr(hi), _c.ptr(lo), _c.cur_stream()), "conv_weight")
+        return SplitMat(hi, lo, O, 9 * I, 9 * Ip)
+    return _cached(conv_weight, "conv", mk)
+
+
+def conv3x3_relu(xs, B, H, W, Cin, conv, want_f32=False, want_split=True):
+    """xs: (hi, lo) NHWC bf16 tensors [B,H,W,Cin]; conv: nn.Conv2d(3x3, pad 1). ReLU fused.
+    Returns (y_f32 NHWC or None, (yhi, ylo) or None)."""
+    wsp = _conv_weight_split(conv.weight)
+    Cout = conv.weight.size(0)
+    dev = xs[0].device
+    y = torch.empty(B, H, W, Cout, dtype=torch.float32, device=dev) if want_f32 else None
+    yh = torch.empty(B, H, W, Cout, dtype=torch.bfloat16, device=dev) if want_split else None
+    yl = torch.empty_like(yh) if want_split else None
+    with torch.cuda.device(dev):
+        rc = _c.load().mb200_conv3x3_bf16x3(_c.ptr(xs[0]), _c.ptr(xs[1]), _c.ptr(wsp.hi), _c.ptr(wsp.lo), B, H, W, Cin,
+                                            Cout, _c.ptr(conv.bias.detach()) if conv.bias is not None else None, 1,
+                                            _c.ptr(y), _c.ptr(yh), _c.ptr(yl), _c.cur_stream())
+    _c.check(rc, "mb200_conv3x3_bf16x3")
+    return y, ((yh, yl) if want_split else None)
+
+
+def maxpool2(xs, B, H, W, C):
+    dev = xs[0].device
+    yh = torch.empty(B, H // 2, W // 2, C, dtype=torch.bfloat16, device=dev)
+    yl = torch.empty_like(yh)
+    with torch.cuda.device(dev):
+        _c.check(_c.load().mb200_maxpool2_nhwc_split(_c.ptr(xs[0]), _c.ptr(xs[1]), B, H, W, C, _c.ptr(yh), _c.ptr(yl),
+                                                     _c.cur_stream()), "mb200_maxpool2_nhwc_split")
+    return (yh, yl)
+
+
+def vgg_features_forward(x, convs):
+    """x [B,3,H,W] fp32 NCHW; convs: the 13 nn.Conv2d of VGG16 `features` minus the last max-pool
+    (load_vgg, lib/object_detector.py:623-633). Returns conv5_3+ReLU as NHWC fp32 [B,H/16,W/16,512].
+    Forward only (the detector is frozen in train_rels.py:51-52 and its output is detached)."""
+    _c.require_cuda(x)
+    x = x.contiguous().float()
+    B, _, H, W = x.shape
+    dev = x.device
+    lib = _c.load()
+    # stem: explicit im2col (K = 27 -> 64) + plain GEMM with fused bias/ReLU, output NHWC pair
+    a_hi = torch.empty(B * H * W, 64, dtype=torch.bfloat16, device=dev); a_lo = torch.empty_like(a_hi)
+    with torch.cuda.device(dev):
+        _c.check(lib.mb200_im2col3_split(_c.ptr(x), B, H, W, _c.ptr(a_hi), _c.ptr(a_lo), _c.cur_stream()), "im2col3")
+    w0 = _conv_weight_split(convs[0].weight)
+    cur = gemm(SplitMat(a_hi, a_lo, B * H * W, 27, 64), w0, bias=convs[0].bias.detach(), relu=True,
+               want_f32=False, want_split=True)
+    C = convs[0].weight.size(0)
+    xs = (cur.hi.view(B, H, W, C), cur.lo.view(B, H, W, C))
+    ci = 1
+    out = None
+    for li, v in enumerate(VGG16_CFG[1:], start=1):
+        if v == 'M':
+            xs = maxpool2(xs, B, H, W, C)
+            H, W = H // 2, W // 2
+            continue
+        last = ci == len(convs) - 1
+        out, xs = conv3x3_relu(xs, B, H, W, C, convs[ci], want_f32=last, want_split=not last)
+        C = v
+        ci += 1
+    return out

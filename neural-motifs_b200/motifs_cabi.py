@@ -34,6 +34,15 @@ SIGNATURES = {
     "mb200_highway_lstm_scratch_floats": (c_size_t, [c_int, c_int, c_int]),
     "mb200_highway_lstm_forward": (c_int, [c_int] * 5 + [P] * 9 + [P]),
     "mb200_highway_lstm_backward": (c_int, [c_int] * 5 + [P] * 14 + [c_int, P, P]),
+    "mb200_gemm_workspace_floats": (c_longlong, [c_int, c_int, c_int]),
+    "mb200_gemm_bf16x3": (c_int, [P, P, P, P, c_int, c_int, c_int, P, c_int, P, c_longlong, P, P, c_longlong, P, P]),
+    "mb200_conv3x3_bf16x3": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, P, c_int, P, P, P, P]),
+    "mb200_split_bf16": (c_int, [P, c_longlong, c_int, c_longlong, c_int, P, P, P]),
+    "mb200_split_transpose_bf16": (c_int, [P, c_int, c_int, c_longlong, c_int, P, P, P]),
+    "mb200_conv_weight_split": (c_int, [P, c_int, c_int, c_int, P, P, P]),
+    "mb200_im2col3_split": (c_int, [P, c_int, c_int, c_int, P, P, P]),
+    "mb200_stem_weight_split": (c_int, [P, c_int, P, P, P]),
+    "mb200_maxpool2_nhwc_split": (c_int, [P, P, c_int, c_int, c_int, c_int, P, P, P]),
     "mb200_sgemm": (c_int, [c_int, c_int, c_int, c_int, c_int, c_float, P, c_int, P, c_int, c_float, P, c_int, P]),
 }
 

@@ -1,0 +1,100 @@
+"""GPU parity of the tcgen05 bf16x3 GEMM / conv path against fp64 references of the same op.
+Tolerance: the scheme keeps ~16 mantissa bits per operand with fp32 accumulation; the asserted
+bound is 3e-5 of the output's max magnitude (a single-pass bf16 GEMM sits near 4e-3, tf32 near 5e-4)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def relerr(a, b):
+    return float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (128, 128, 256), (120, 4096, 1000), (1536, 51, 4096),
+                                   (300, 151, 4424), (257, 640, 712), (2000, 3072, 512)])
+def test_gemm_bf16x3_vs_fp64(cuda, M, N, K):
+    from lib import tc_ops
+    torch.manual_seed(M + N + K)
+    x = torch.randn(M, K, device=cuda)
+    w = torch.randn(N, K, device=cuda) / K ** 0.5
+    b = torch.randn(N, device=cuda)
+    ref = x.double() @ w.double().t() + b.double()
+    y = tc_ops.gemm(tc_ops.split_rows(x), tc_ops.split_rows(w), bias=b)
+    assert relerr(y, ref) < 3e-5, relerr(y, ref)
+    yr, ys = tc_ops.gemm(tc_ops.split_rows(x), tc_ops.split_rows(w), bias=b, relu=True, want_f32=True, want_split=True)
+    assert relerr(yr, ref.clamp_min(0)) < 3e-5
+    rec = ys.hi[:, :N].float() + ys.lo[:, :N].float()
+    assert relerr(rec, ref.clamp_min(0)) < 3e-5
+
+
+def test_gemm_split_k_path(cuda):
+    """Skinny M with a long K takes the split-K route (fc6 at 120 rois: K = 25088)."""
+    from lib import tc_ops
+    import motifs_cabi as C
+    torch.manual_seed(0)
+    M, N, K = 120, 1024, 25088
+    assert C.load().mb200_gemm_workspace_floats(M, N, K) > 0
+    x = torch.randn(M, K, device=cuda); w = torch.randn(N, K, device=cuda) / K ** 0.5
+    ref = x.double() @ w.double().t()
+    assert relerr(tc_ops.gemm(tc_ops.split_rows(x), tc_ops.split_rows(w)), ref) < 3e-5
+
+
+def test_linear_tc_autograd(cuda):
+    from lib import tc_ops
+    torch.manual_seed(1)
+    x = torch.randn(200, 712, device=cuda, requires_grad=True)
+    lin = torch.nn.Linear(712, 300).to(cuda)
+    y = tc_ops.linear_tc(x, lin.weight, lin.bias)
+    g = torch.randn_like(y)
+    y.backward(g)
+    xd = x.detach().double().requires_grad_(True)
+    wd = lin.weight.detach().double().requires_grad_(True)
+    bd = lin.bias.detach().double().requires_grad_(True)
+    yd = xd @ wd.t() + bd
+    yd.backward(g.double())
+    assert relerr(y.detach(), yd.detach()) < 3e-5
+    assert relerr(x.grad, xd.grad) < 3e-5
+    assert relerr(lin.weight.grad, wd.grad) < 3e-5
+    assert relerr(lin.bias.grad, bd.grad) < 1e-5
+    # the weight-split cache must notice an in-place update
+    with torch.no_grad():
+        lin.weight.add_(1.0)
+    y2 = tc_ops.linear_tc(x.detach(), lin.weight, lin.bias)
+    assert relerr(y2, x.detach().double() @ lin.weight.detach().double().t() + lin.bias.detach().double()) < 3e-5
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(1, 8, 16, 64, 128), (2, 37, 37, 512, 512), (1, 74, 74, 256, 512), (2, 20, 50, 64, 64)])
+def test_conv3x3_vs_fp64(cuda, B, H, W, Cin, Cout):
+    from lib import tc_ops
+    torch.manual_seed(B * H + W)
+    conv = torch.nn.Conv2d(Cin, Cout, 3, padding=1).to(cuda)
+    x = torch.randn(B, Cin, H, W, device=cuda)
+    ref = torch.nn.functional.conv2d(x.double(), conv.weight.double(), conv.bias.double(), padding=1).clamp_min(0)
+    xn = x.permute(0, 2, 3, 1).contiguous().view(-1, Cin)
+    xs = tc_ops.split_rows(xn)
+    y, ysplit = tc_ops.conv3x3_relu((xs.hi.view(B, H, W, Cin), xs.lo.view(B, H, W, Cin)), B, H, W, Cin, conv,
+                                    want_f32=True, want_split=True)
+    refn = ref.permute(0, 2, 3, 1)
+    assert relerr(y, refn) < 3e-5, relerr(y, refn)
+    assert relerr(ysplit[0].float() + ysplit[1].float(), refn) < 3e-5
+
+
+def test_maxpool_and_vgg_features_vs_torch(cuda):
+    """Whole frozen VGG16 feature extractor (13 convs, 4 pools) vs torch fp64 on a small image."""
+    from lib import tc_ops
+    from torchvision.models.vgg import vgg16
+    torch.manual_seed(3)
+    feats = vgg16(weights=None).features
+    del feats._modules['30']
+    feats = feats.to(cuda).eval()
+    x = torch.randn(2, 3, 96, 160, device=cuda)
+    convs = [m for m in feats if isinstance(m, torch.nn.Conv2d)]
+    with torch.no_grad():
+        ref = feats.double()(x.double()).float()
+        feats.float()
+        out = tc_ops.vgg_features_forward(x, convs)
+    assert tuple(out.shape) == (2, 6, 10, 512)
+    # 13 stacked layers: north-star bar is 1e-3; the bf16x3 path should sit near 1e-4
+    assert relerr(out.permute(0, 3, 1, 2), ref) < 3e-4, relerr(out.permute(0, 3, 1, 2), ref)
