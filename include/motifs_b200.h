@@ -78,6 +78,11 @@ int mb200_roi_align_forward_nhwc(const float* image_nhwc, const float* boxes_ptr
                                  int image_height, int image_width, int crop_height, int crop_width,
                                  int depth, float extrapolation_value, float* crops_nhwc, cudaStream_t stream);
 
+/* Same, but the output is the reference's [num_boxes, depth, crop_h, crop_w] layout (depth % 4 == 0). */
+int mb200_roi_align_forward_nhwc_to_nchw(const float* image_nhwc, const float* boxes_ptr, int num_boxes, int batch,
+                                         int image_height, int image_width, int crop_height, int crop_width,
+                                         int depth, float extrapolation_value, float* crops_nchw, cudaStream_t stream);
+
 /* Segmented greedy NMS entirely on the device (no D2H). See csrc/nms.cu. */
 long long mb200_nms_mask_words(const int* seg_sizes_host, int num_segments);
 int mb200_nms_segmented(const float* boxes_dev, const int* seg_off_dev, const long long* mask_off_dev,
@@ -114,6 +119,16 @@ int mb200_highway_lstm_backward(int inputSize, int hiddenSize, int miniBatch, in
                                 const float* T, const float* gates_out, const float* dropout_in,
                                 float* h_out_grad, float* x_grad, float* T_grad, float* bias_grad,
                                 int do_weight_grad, float* dG_scratch, cudaStream_t stream);
+
+/* One layer of the recurrence with the input projection P [T,B,6H] supplied by the caller (hoisted
+ * tensor-core GEMM); gates may alias P. Backward fills dG [T,B,6H]; dX/dW/db are the caller's GEMMs. */
+int mb200_highway_lstm_layer_forward(int hiddenSize, int miniBatch, int seqLength, int dir, const float* P,
+                                     const float* Wh, const float* bias, const float* dropout, float* h, float* c,
+                                     float* gates, const int* lengths_dev, cudaStream_t stream);
+int mb200_highway_lstm_layer_backward(int hiddenSize, int miniBatch, int seqLength, int dir, const float* out_grad,
+                                      const float* Wh, const float* h, const float* c, const float* gates,
+                                      const float* dropout, float* h_grad, float* c_grad, float* dG,
+                                      const int* lengths_dev, cudaStream_t stream);
 
 /* Exact-fp32 SIMT GEMM, row-major, C = alpha*op(A)*op(B) + beta*C (replaces the cublasSgemm calls
  * of highway_lstm_kernel.cu:441-465 for small shapes; cross-check for the tcgen05 path). */

@@ -396,6 +396,49 @@ int mb200_highway_lstm_backward(int inputSize, int hiddenSize, int miniBatch, in
   return MB200_OK;
 }
 
+
+// Single layer, projection already done (P = x_t W_i for every step, [T,B,6H]): just the persistent
+// recurrence. h / c [T+1,B,H] zero on entry; gates may alias P (in place) or be NULL.
+int mb200_highway_lstm_layer_forward(int hiddenSize, int miniBatch, int seqLength, int dir, const float* P,
+                                     const float* Wh, const float* bias, const float* dropout, float* h, float* c,
+                                     float* gates, const int* lengths_dev, cudaStream_t stream) {
+  const int H = hiddenSize, B = miniBatch, TT = seqLength;
+  if (H <= 0 || B <= 0 || TT <= 0) return MB200_OK;
+  if (H % kUJ != 0 || (H % 4) != 0) return MB200_ERR_UNSUPPORTED;
+  const int grid = H / kUJ;
+  const size_t smem = fwd_smem_bytes(H, B);
+  int rc = check_coop((const void*)lstm_fwd_kernel, grid, smem);
+  if (rc != MB200_OK) return rc;
+  FwdArgs a;
+  a.H = H; a.B = B; a.T = TT; a.dir = dir; a.training = gates != nullptr;
+  a.P = P; a.Wh = Wh; a.bias = bias; a.dropout = dropout; a.h = h; a.c = c; a.gates = gates; a.lengths = lengths_dev;
+  void* args[] = {&a};
+  MB200_CHECK(cudaLaunchCooperativeKernel((const void*)lstm_fwd_kernel, dim3(grid), dim3(kThreads), args, smem, stream));
+  return MB200_OK;
+}
+
+// Single layer backward through time: fills dG [T,B,6H] (zeroed here), h_grad / c_grad [T+1,B,H]
+// (zero on entry). The caller turns dG into dX, dW_i, dW_h, db with large GEMMs.
+int mb200_highway_lstm_layer_backward(int hiddenSize, int miniBatch, int seqLength, int dir, const float* out_grad,
+                                      const float* Wh, const float* h, const float* c, const float* gates,
+                                      const float* dropout, float* h_grad, float* c_grad, float* dG,
+                                      const int* lengths_dev, cudaStream_t stream) {
+  const int H = hiddenSize, B = miniBatch, TT = seqLength;
+  if (H <= 0 || B <= 0 || TT <= 0) return MB200_OK;
+  if (H % kUJ != 0 || (H % 4) != 0) return MB200_ERR_UNSUPPORTED;
+  const int grid = H / kUJ;
+  const size_t smem = bwd_smem_bytes(H, B);
+  int rc = check_coop((const void*)lstm_bwd_kernel, grid, smem);
+  if (rc != MB200_OK) return rc;
+  MB200_CHECK(cudaMemsetAsync(dG, 0, (size_t)TT * B * 6 * H * sizeof(float), stream));
+  BwdArgs a;
+  a.H = H; a.B = B; a.T = TT; a.dir = dir; a.out_grad = out_grad; a.Wh = Wh; a.h = h; a.c = c; a.gates = gates;
+  a.dropout = dropout; a.h_grad = h_grad; a.c_grad = c_grad; a.dG = dG; a.lengths = lengths_dev;
+  void* args[] = {&a};
+  MB200_CHECK(cudaLaunchCooperativeKernel((const void*)lstm_bwd_kernel, dim3(grid), dim3(kThreads), args, smem, stream));
+  return MB200_OK;
+}
+
 // ---- drop-in launchers (highway_lstm_kernel.h:7-9): host lengths, internal scratch.
 void highway_lstm_forward_ongpu(int inputSize, int hiddenSize, int miniBatch, int numLayers, int seqLength,
                                 float* x, int* lengths, float* h_data, float* c_data, float* tmp_i,

@@ -81,3 +81,20 @@ def roi_align_nhwc(features_nhwc, rois, aligned_height, aligned_width, spatial_s
                                               aligned_height, aligned_width, C, 0.0, _c.ptr(out), _c.cur_stream())
     _c.check(rc, "mb200_roi_align_forward_nhwc")
     return out
+
+
+def roi_align_from_nhwc(features_nhwc, rois, aligned_height, aligned_width, spatial_scale):
+    """Pipeline variant (no autograd): features [B,H,W,C] (C % 4 == 0) -> the reference's
+    [N,C,ah,aw] layout, so fc6's flatten order (c, y, x) is unchanged."""
+    _c.require_cuda(features_nhwc, rois)
+    B, H, W, C = features_nhwc.shape
+    rois_n = normalize_rois(rois.detach().contiguous().float(), H, W, spatial_scale)
+    out = torch.empty(rois.size(0), C, aligned_height, aligned_width, device=features_nhwc.device,
+                      dtype=torch.float32)
+    lib = _c.load()
+    with torch.cuda.device(features_nhwc.device):
+        rc = lib.mb200_roi_align_forward_nhwc_to_nchw(_c.ptr(features_nhwc), _c.ptr(rois_n), rois.size(0), B, H, W,
+                                                      aligned_height, aligned_width, C, 0.0, _c.ptr(out),
+                                                      _c.cur_stream())
+    _c.check(rc, "mb200_roi_align_forward_nhwc_to_nchw")
+    return out

@@ -1,0 +1,74 @@
+"""Union-box features — same surface as the reference's lib/get_union_boxes.py:15-93:
+`UnionBoxesAndFeats(pooling_size, stride, dim)(fmap, rois, union_inds)` = RoIAlign over the union
+roi of each (subject, object) pair + a small conv net over the pair's two rasterised box masks.
+
+The reference goes D2H -> Cython rasteriser on the CPU -> H2D in the middle of forward (:47-50);
+here union rois, pair boxes and the [N,2,27,27] masks are produced on the device (csrc/boxes.cu)."""
+import torch
+from torch import nn
+from torch.nn.modules.module import Module
+
+import motifs_cabi as _c
+from config import BATCHNORM_MOMENTUM
+from lib.draw_rectangles.draw_rectangles import draw_union_boxes_cuda
+from lib.fpn.roi_align.functions.roi_align import RoIAlignFunction, roi_align_from_nhwc
+
+
+def union_rois_and_pairs(rois, union_inds):
+    """rois [N,5], union_inds [R,2] int64 -> (union rois [R,5], pair boxes [R,8]) in one kernel
+    (get_union_boxes.py:82-87 and the gather of :47)."""
+    _c.require_cuda(rois, union_inds)
+    rois = rois.detach().contiguous().float()
+    union_inds = union_inds.contiguous().long()
+    R = union_inds.size(0)
+    u = torch.empty(R, 5, device=rois.device, dtype=torch.float32)
+    pb = torch.empty(R, 8, device=rois.device, dtype=torch.float32)
+    with torch.cuda.device(rois.device):
+        _c.check(_c.load().mb200_union_rois(_c.ptr(rois), _c.ptr(union_inds), R, _c.ptr(u), _c.ptr(pb), _c.cur_stream()),
+                 "mb200_union_rois")
+    return u, pb
+
+
+def union_boxes(fmap, rois, union_inds, pooling_size=14, stride=16):
+    """get_union_boxes.py:72-93 (gradients reach fmap through RoIAlign backward)."""
+    assert union_inds.size(1) == 2
+    u, _ = union_rois_and_pairs(rois, union_inds)
+    return RoIAlignFunction(pooling_size, pooling_size, spatial_scale=1 / stride)(fmap, u)
+
+
+class UnionBoxesAndFeats(Module):
+    def __init__(self, pooling_size=7, stride=16, dim=256, concat=False, use_feats=True):
+        super().__init__()
+        self.pooling_size = pooling_size
+        self.stride = stride
+        self.dim = dim
+        self.use_feats = use_feats
+        self.conv = nn.Sequential(
+            nn.Conv2d(2, dim // 2, kernel_size=7, stride=2, padding=3, bias=True),
+            nn.ReLU(inplace=True),
+            nn.BatchNorm2d(dim // 2, momentum=BATCHNORM_MOMENTUM),
+            nn.MaxPool2d(kernel_size=3, stride=2, padding=1),
+            nn.Conv2d(dim // 2, dim, kernel_size=3, stride=1, padding=1, bias=True),
+            nn.ReLU(inplace=True),
+            nn.BatchNorm2d(dim, momentum=BATCHNORM_MOMENTUM),
+        )
+        self.concat = concat
+
+    def forward(self, fmap, rois, union_inds, fmap_nhwc=None):
+        """fmap [B,C,H,W]; when the caller also holds the NHWC copy the backbone produced
+        (`fmap_nhwc`, no gradient needed) the pooled features come from the channel-vectorised kernel."""
+        u, pair_boxes = union_rois_and_pairs(rois, union_inds)
+        if fmap_nhwc is not None and not fmap.requires_grad:
+            union_pools = roi_align_from_nhwc(fmap_nhwc, u, self.pooling_size, self.pooling_size, 1 / self.stride)
+        else:
+            union_pools = RoIAlignFunction(self.pooling_size, self.pooling_size, spatial_scale=1 / self.stride)(fmap, u)
+        if not self.use_feats:
+            return union_pools.detach()
+        rects = draw_union_boxes_cuda(pair_boxes, self.pooling_size * 4 - 1, offset=0.5)
+        # The mask conv net (7x7 s2 + 3x3) still runs on cuDNN this round; TF32 is
+        # switched off so it stays inside the fp32 parity bar (TF32 alone costs ~1e-3 here).
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+            conv_out = self.conv(rects)
+        if self.concat:
+            return torch.cat((union_pools, conv_out), 1)
+        return union_pools + conv_out

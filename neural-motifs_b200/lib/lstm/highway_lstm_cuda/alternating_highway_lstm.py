@@ -36,58 +36,69 @@ def block_orthogonal(tensor, split_sizes, gain=1.0):
     return tensor
 
 
-class _AlternatingHighwayLSTMFunction(Function):
-    @staticmethod
-    def forward(ctx, inputs, weight, bias, dropout_mask, lengths_dev, hidden_size, num_layers, save_gates):
-        _c.require_cuda(inputs, weight, bias, dropout_mask, lengths_dev)
-        inputs = inputs.contiguous()
-        T, B, In = inputs.shape
-        H, L = hidden_size, num_layers
-        dev = inputs.device
-        state_acc = torch.zeros(L, T + 1, B, H, device=dev, dtype=torch.float32)
-        memory_acc = torch.zeros(L, T + 1, B, H, device=dev, dtype=torch.float32)
-        gates = torch.empty(L, T, B, 6 * H, device=dev, dtype=torch.float32) if save_gates else None
-        scratch = None if save_gates else torch.empty(T, B, 6 * H, device=dev, dtype=torch.float32)
-        lib = _c.load()
-        with torch.cuda.device(dev):
-            rc = lib.mb200_highway_lstm_forward(In, H, B, L, T, _c.ptr(inputs), _c.ptr(lengths_dev),
-                                                _c.ptr(state_acc), _c.ptr(memory_acc), _c.ptr(weight), _c.ptr(bias),
-                                                _c.ptr(dropout_mask), _c.ptr(gates), _c.ptr(scratch), _c.cur_stream())
-        _c.check(rc, "mb200_highway_lstm_forward")
-        ctx.dims = (T, B, In, H, L)
-        ctx.have_gates = save_gates
-        if save_gates:
-            ctx.save_for_backward(inputs, lengths_dev, weight, bias, state_acc, memory_acc, dropout_mask, gates)
-        # output = last layer, all slots but the initial state (:104-108)
-        return state_acc[-1, 1:, :, :]
+class _HighwayLayerFunction(Function):
+    """One layer of the recurrence on the persistent kernel (csrc/lstm.cu). P [T,B,6H] is the hoisted
+    input projection (a tcgen05 GEMM, lib/tc_ops.py); the kernel overwrites it in place with the six
+    gate activations, which is what backward needs (elementWise_fp/bp, highway_lstm_kernel.cu:46-160)."""
 
     @staticmethod
-    def backward(ctx, grad_output):
-        if not ctx.have_gates:
-            raise _c.MotifsB200Error("AlternatingHighwayLSTM backward needs the gates saved in forward")
-        inputs, lengths_dev, weight, bias, state_acc, memory_acc, dropout_mask, gates = ctx.saved_tensors
-        T, B, In, H, L = ctx.dims
-        dev = inputs.device
-        grad_output = grad_output.contiguous()
-        need_w = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
-        grad_input = torch.empty_like(inputs)
-        grad_state = torch.zeros_like(state_acc)
-        grad_memory = torch.zeros_like(memory_acc)
-        grad_weight = torch.zeros_like(weight)
-        grad_bias = torch.zeros_like(bias)
-        h_out_grad = torch.empty(L, T, B, H, device=dev, dtype=torch.float32)
-        dG = torch.empty(T, B, 6 * H, device=dev, dtype=torch.float32)
+    def forward(ctx, P, Wh, bias, dropout, lengths_dev, direction, save_gates):
+        _c.require_cuda(P, Wh, bias, dropout, lengths_dev)
+        P = P.contiguous()
+        Wh = Wh.contiguous()
+        bias = bias.contiguous()
+        T, B, H6 = P.shape
+        H = H6 // 6
+        dev = P.device
+        h = torch.zeros(T + 1, B, H, device=dev, dtype=torch.float32)
+        c = torch.zeros(T + 1, B, H, device=dev, dtype=torch.float32)
         lib = _c.load()
         with torch.cuda.device(dev):
-            rc = lib.mb200_highway_lstm_backward(In, H, B, L, T, _c.ptr(grad_output), _c.ptr(lengths_dev),
-                                                 _c.ptr(grad_state), _c.ptr(grad_memory), _c.ptr(inputs),
-                                                 _c.ptr(state_acc), _c.ptr(memory_acc), _c.ptr(weight), _c.ptr(gates),
-                                                 _c.ptr(dropout_mask), _c.ptr(h_out_grad), _c.ptr(grad_input),
-                                                 _c.ptr(grad_weight), _c.ptr(grad_bias), 1 if need_w else 0,
-                                                 _c.ptr(dG), _c.cur_stream())
-        _c.check(rc, "mb200_highway_lstm_backward")
-        return (grad_input, grad_weight if need_w else None, grad_bias if need_w else None,
-                None, None, None, None, None)
+            rc = lib.mb200_highway_lstm_layer_forward(H, B, T, direction, _c.ptr(P), _c.ptr(Wh), _c.ptr(bias),
+                                                      _c.ptr(dropout), _c.ptr(h), _c.ptr(c),
+                                                      _c.ptr(P) if save_gates else None, _c.ptr(lengths_dev),
+                                                      _c.cur_stream())
+        _c.check(rc, "mb200_highway_lstm_layer_forward")
+        ctx.direction = direction
+        ctx.have_gates = save_gates
+        if save_gates:
+            ctx.save_for_backward(P, Wh, h, c, dropout, lengths_dev)
+        return h[1:]
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        if not ctx.have_gates:
+            raise _c.MotifsB200Error("highway LSTM backward needs the gates saved in forward")
+        from lib import tc_ops
+        gates, Wh, h, c, dropout, lengths_dev = ctx.saved_tensors
+        T, B, H6 = gates.shape
+        H = H6 // 6
+        dev = gates.device
+        grad_out = grad_out.contiguous()
+        h_grad = torch.zeros_like(h)
+        c_grad = torch.zeros_like(c)
+        dG = torch.empty_like(gates)
+        lib = _c.load()
+        with torch.cuda.device(dev):
+            rc = lib.mb200_highway_lstm_layer_backward(H, B, T, ctx.direction, _c.ptr(grad_out), _c.ptr(Wh), _c.ptr(h),
+                                                       _c.ptr(c), _c.ptr(gates), _c.ptr(dropout), _c.ptr(h_grad),
+                                                       _c.ptr(c_grad), _c.ptr(dG), _c.ptr(lengths_dev), _c.cur_stream())
+        _c.check(rc, "mb200_highway_lstm_layer_backward")
+        dWh = dbias = None
+        dG2 = dG.view(T * B, 6 * H)
+        if ctx.needs_input_grad[1]:
+            # dW_h = Hprev^T dG[:, :5H] (:329-340): even layers read slot t, odd layers slot t+2 (t <= T-2)
+            if ctx.direction == 0:
+                hp, g5 = h[:T].reshape(T * B, H), dG2[:, :5 * H]
+            else:
+                hp, g5 = h[2:].reshape((T - 1) * B, H), dG2[:(T - 1) * B, :5 * H]
+            if hp.size(0) > 0:
+                dWh = tc_ops.gemm(tc_ops.split_transposed(hp), tc_ops.split_transposed(g5))
+            else:
+                dWh = torch.zeros_like(Wh)
+        if ctx.needs_input_grad[2]:
+            dbias = dG2[:, :5 * H].sum(0)
+        return dG, dWh, dbias, None, None, None, None
 
 
 class AlternatingHighwayLSTM(torch.nn.Module):
@@ -142,7 +153,21 @@ class AlternatingHighwayLSTM(torch.nn.Module):
         lengths_dev = lengths.to(device=dev, dtype=torch.int32)
         save_gates = torch.is_grad_enabled() and (padded.requires_grad or self.weight.requires_grad
                                                   or self.bias.requires_grad)
-        output = _AlternatingHighwayLSTMFunction.apply(padded, self.weight, self.bias, dropout_weights, lengths_dev,
-                                                       self.hidden_size, self.num_layers, save_gates)
+        from lib import tc_ops
+        H = self.hidden_size
+        x = padded.contiguous()
+        off = 0
+        for layer in range(self.num_layers):
+            insz = self.input_size if layer == 0 else H
+            wi = self.weight[off:off + insz * 6 * H].view(insz, 6 * H)
+            off += insz * 6 * H
+            wh = self.weight[off:off + H * 5 * H].view(H, 5 * H)
+            off += H * 5 * H
+            b = self.bias[layer * 5 * H:(layer + 1) * 5 * H]
+            # hoisted input projection for every timestep at once (the reference does one small
+            # cublasSgemm per step, highway_lstm_kernel.cu:441-452)
+            P = tc_ops.matmul_tc(x.view(T * B, insz), wi, self.weight, ("wi", layer)).view(T, B, 6 * H)
+            x = _HighwayLayerFunction.apply(P, wh, b, dropout_weights[layer], lengths_dev, layer % 2, save_gates)
+        output = x
         output = pack_padded_sequence(output, lengths, batch_first=False)
         return output, None

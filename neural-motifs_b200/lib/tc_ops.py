@@ -100,6 +100,18 @@ def _cached(param, kind, maker):
     return val
 
 
+def _cached_view(base, tag, view, maker):
+    """Like _cached, for a view (slice) of the flat parameter `base`; `tag` names the slice."""
+    key = (id(base), tag)
+    ver = (base.data_ptr(), base._version, tuple(view.shape))
+    hit = _cache.get(key)
+    if hit is not None and hit[0] == ver:
+        return hit[1]
+    val = maker(view.detach())
+    _cache[key] = (ver, val)
+    return val
+
+
 def weight_split(weight):          # [N,K] -> B operand of  x @ W^T
     return _cached(weight, "rows", split_rows)
 
@@ -133,6 +145,33 @@ class _LinearTC(Function):
         if ctx.has_bias and ctx.needs_input_grad[2]:
             gb = gy.sum(0)
         return gx, gw, gb
+
+
+class _MatmulTC(Function):
+    """y = x @ w with w [K,N] a view of the flat parameter `base` (highway-LSTM weight layout,
+    alternating_highway_lstm.py:212-221). `tag` identifies the view for the split cache."""
+
+    @staticmethod
+    def forward(ctx, x, w, base, tag):
+        y = gemm(split_rows(x.detach()), _cached_view(base, (tag, "T"), w, split_transposed))
+        ctx.save_for_backward(x, w)
+        ctx.base, ctx.tag = base, tag
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w = ctx.saved_tensors
+        gy = gy.contiguous()
+        gx = gw = None
+        if ctx.needs_input_grad[0]:
+            gx = gemm(split_rows(gy), _cached_view(ctx.base, (ctx.tag, "R"), w, split_rows))   # gy @ w^T
+        if ctx.needs_input_grad[1]:
+            gw = gemm(split_transposed(x.detach()), split_transposed(gy))                      # x^T @ gy
+        return gx, gw, None, None
+
+
+def matmul_tc(x, w, base, tag):
+    return _MatmulTC.apply(x, w, base, tag)
 
 
 def linear_tc(x, weight, bias=None):
@@ -199,7 +238,7 @@ def maxpool2(xs, B, H, W, C):
     return (yh, yl)
 
 
-def vgg_features_forward(x, convs):
+def vgg_features_forward(x, convs, want_last_split=False):
     """x [B,3,H,W] fp32 NCHW; convs: the 13 nn.Conv2d of VGG16 `features` minus the last max-pool
     (load_vgg, lib/object_detector.py:623-633). Returns conv5_3+ReLU as NHWC fp32 [B,H/16,W/16,512].
     Forward only (the detector is frozen in train_rels.py:51-52 and its output is detached)."""
@@ -225,7 +264,7 @@ def vgg_features_forward(x, convs):
             H, W = H // 2, W // 2
             continue
         last = ci == len(convs) - 1
-        out, xs = conv3x3_relu(xs, B, H, W, C, convs[ci], want_f32=last, want_split=not last)
+        out, xs = conv3x3_relu(xs, B, H, W, C, convs[ci], want_f32=last, want_split=(not last) or want_last_split)
         C = v
         ci += 1
-    return out
+    return out, (xs if want_last_split else None)

@@ -24,6 +24,9 @@ SIGNATURES = {
     "mb200_compiled_arch": (c_int, []),
     "mb200_device_ok": (c_int, []),
     "mb200_roi_align_forward_nhwc": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, P, P]),
+    "mb200_roi_align_forward_nhwc_to_nchw": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, P, P]),
+    "mb200_highway_lstm_layer_forward": (c_int, [c_int] * 4 + [P] * 9),
+    "mb200_highway_lstm_layer_backward": (c_int, [c_int] * 4 + [P] * 11),
     "mb200_nms_mask_words": (c_longlong, [P, c_int]),
     "mb200_nms_segmented": (c_int, [P, P, P, c_int, c_int, c_float, c_int, P, P, P, P]),
     "mb200_bbox_overlaps_f32": (c_int, [P, c_int, P, c_int, P, P]),
