@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""bench.py — MotifNet-SGCls training throughput (images/sec), BASELINE.json's headline metric.
+
+    python bench.py --gpus N --steps K --warmup W            # this framework, one rank per GPU
+    python bench.py --impl reference --gpus N --steps K --warmup W   # CPU reference arm (oracle port)
+
+Workload (BASELINE.json configs[1]): models/train_rels.py step of MotifNet SGCls — VGG16 backbone
+(frozen), batch 6 x 3 x 592 x 592 synthetic images per GPU, 20 GT boxes and 15 GT relations per image
+(-> 1536 sampled relation triples), forward + backward + grad-clip + SGD(momentum) step, fp32 semantics.
+A "step" is one such training step on one batch per GPU (weak scaling: 6 images per GPU).
+
+Timing: W >= 3 untimed warm-up steps, then exactly K steps bracketed by barrier + cuda synchronize
+on both sides, CUDA events on the launching stream, max over ranks. The per-step working set
+(1.7 GB of parameters + 25 MB fresh images + activations) is far larger than the 126 MB L2, so no
+explicit L2 flush is needed (stated in `config`).
+
+One JSON line on rank 0 with `value` (inputs already resident in HBM), `e2e` (through the public
+`detector[blob]` API from pinned host buffers, H2D of the batch and D2H of the loss inside the timed
+region), `roofline` (dominant kernel = the tcgen05 bf16x3 GEMM/conv, algorithmic fp32 FLOPs per
+launch / CUDA-event duration vs the measured bf16 peak), `cpu_baseline` (oracle port on host cores,
+bounded sample) and `clocks`.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "neural-motifs_b200"))
+
+BATCH_PER_GPU = 6
+BOXES, RELS = 20, 15
+METRIC = "MotifNet-SGCls train images/sec"
+UNIT = "img/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.proc, self.lines, self.gpu = None, [], gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons, power = [], [], set(), []
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------ model setup
+def build_model(device, seed=0):
+    import torch
+    from lib.rel_model import RelModel
+    from dataloaders.synthetic import synthetic_model_state
+    classes = ['__background__'] + ['obj%d' % i for i in range(150)]
+    rels = ['__background__'] + ['rel%d' % i for i in range(50)]
+    torch.manual_seed(seed)
+    # scripts/train_models_sgcls.sh:19-21
+    m = RelModel(classes, rels, mode='sgcls', num_gpus=1, require_overlap_det=True, use_resnet=False, order='leftright',
+                 nl_edge=4, nl_obj=2, hidden_dim=512, use_proposals=False, pass_in_obj_feats_to_decoder=False,
+                 pass_in_obj_feats_to_edge=False, pooling_dim=4096, rec_dropout=0.1, use_bias=True, use_tanh=False,
+                 limit_vision=False)
+    synthetic_model_state(m, seed)
+    with torch.no_grad():
+        for mod in m.modules():
+            if isinstance(mod, torch.nn.Conv2d):
+                torch.nn.init.kaiming_normal_(mod.weight, nonlinearity='relu')
+    for p in m.detector.parameters():       # models/train_rels.py:51-52
+        p.requires_grad = False
+    return m.to(device).train()
+
+
+def get_optim(model, lr):
+    """models/train_rels.py:57-70 (SGD branch): fc layers of roi_fmap* at lr/10, momentum 0.9, l2 1e-4."""
+    import torch
+    fc = [p for n, p in model.named_parameters() if n.startswith('roi_fmap') and p.requires_grad]
+    non_fc = [p for n, p in model.named_parameters() if not n.startswith('roi_fmap') and p.requires_grad]
+    return torch.optim.SGD([{'params': fc, 'lr': lr / 10.0}, {'params': non_fc}], weight_decay=1e-4, lr=lr, momentum=0.9)
+
+
+def train_step(model, optimizer, reducer, fwd_tuple=None, blob=None):
+    """models/train_rels.py:118-152 (train_batch): forward, two cross-entropies, backward, clip 5, step."""
+    import torch
+    from torch.nn import functional as F
+    from lib.pytorch_misc import clip_grad_norm
+    result = model[blob] if blob is not None else model(*fwd_tuple)
+    loss = F.cross_entropy(result.rm_obj_dists, result.rm_obj_labels) + \
+        F.cross_entropy(result.rel_dists, result.rel_labels[:, -1])
+    optimizer.zero_grad(set_to_none=True)
+    loss.backward()
+    reducer.all_reduce()
+    clip_grad_norm([(n, p) for n, p in model.named_parameters() if p.grad is not None], max_norm=5.0, clip=True)
+    optimizer.step()
+    return loss
+
+
+# ------------------------------------------------------------------------------------------ b200 arm
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import motifs_cabi
+    from lib import tc_ops
+    from lib.data_parallel import init_from_env, GradAllReducer
+    from dataloaders.synthetic import make_numpy_batch, SyntheticBlob
+
+    rank, world, local = init_from_env("nccl")
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py (impl b200) needs a CUDA device; there is no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    motifs_cabi.load()
+    model = build_model(dev, seed=0)
+    opt = get_optim(model, lr=1e-3 * BATCH_PER_GPU)      # train_rels.py:193: lr * num_gpus * batch_size
+    reducer = GradAllReducer(model.parameters())
+    pool = [make_numpy_batch(BATCH_PER_GPU, seed=100 * rank + i, boxes_per_img=BOXES, rels_per_img=RELS,
+                             image_offset=0) for i in range(4)]
+    blobs = [SyntheticBlob(nb, dev) for nb in pool]
+    for b in blobs:
+        b.scatter()
+    resident = [b[0] for b in blobs]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    W = max(args.warmup, 3)
+    for i in range(W):
+        train_step(model, opt, reducer, fwd_tuple=resident[i % len(resident)])
+    sampler = ClockSampler(local)
+    sampler.start()
+    calls0 = motifs_cabi.LAUNCHER_CALLS
+    ms_res = timed(lambda i: train_step(model, opt, reducer, fwd_tuple=resident[i % len(resident)]), args.steps)
+    calls = motifs_cabi.LAUNCHER_CALLS - calls0
+    # e2e: public API with host buffers; H2D of the batch and D2H of the loss every step
+    losses = []
+
+    def e2e_step(i):
+        losses.append(float(train_step(model, opt, reducer, blob=blobs[i % len(blobs)]).item()))
+
+    for i in range(2):
+        e2e_step(i)
+    ms_e2e = timed(e2e_step, args.steps)
+    clocks = sampler.stop()
+
+    # roofline leg: one extra profiled step, CUDA events around every tensor-core launch
+    tc_ops.PROFILE = []
+    train_step(model, opt, reducer, fwd_tuple=resident[0])
+    torch.cuda.synchronize()
+    prof, tc_ops.PROFILE = tc_ops.PROFILE, None
+    flops = sum(f for _, f, _, _ in prof)
+    tc_ms = sum(a.elapsed_time(b) for _, _, a, b in prof)
+    conv = [(f, a.elapsed_time(b)) for k, f, a, b in prof if k == "conv3x3"]
+    pk, kind = peaks()
+    peak_tf = float(pk.get("bf16_tflops_sustained", pk["bf16_tflops"]))
+    achieved = flops / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
+
+    if rank != 0:
+        return
+    imgs = BATCH_PER_GPU * world * args.steps
+    value = imgs / (ms_res * 1e-3)
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
+        "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "MotifNet SGCls train_rels.py step, VGG16 backbone, batch 6x592x592 per GPU, "
+                               "20 GT boxes + 15 GT rels per image (1536 rel triples), fwd+bwd+clip+SGD",
+                   "global_batch": BATCH_PER_GPU * world, "parallelism": "dp%d" % world,
+                   "arithmetic": "fp32 semantics: tcgen05 bf16x3 split-operand GEMM/conv, fp32 accumulate",
+                   "l2": "per-step working set (1.7 GB params + activations) >> 126 MB L2; 4 rotating batches"},
+        "e2e": {"value": imgs / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
+                "h2d_bytes_per_step": blobs[0].h2d_bytes(), "d2h_bytes_per_step": 4,
+                "api": "RelModel.__getitem__(blob) (models/train_rels.py:137) from pinned host tensors"},
+        "gpu_launches": calls,
+        "gpu_launches_note": "C-ABI launcher calls of libmotifs_b200.so in the timed region (each >= 1 kernel)",
+        "roofline": {"kernel": "gemm_bf16x3_kernel (tcgen05 GEMM + implicit-GEMM 3x3 conv)", "bound": "tensor",
+                     "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+                     "peak_kind": "%s bf16 sustained" % kind, "launches_per_step": len(prof),
+                     "algorithmic_gflop_per_step": flops / 1e9, "kernel_ms_per_step": tc_ms,
+                     "share_of_step": tc_ms / (ms_res / args.steps),
+                     "backbone_conv_tflops": (sum(f for f, _ in conv) / (sum(t for _, t in conv) * 1e-3) / 1e12) if conv else None,
+                     "note": "algorithmic fp32-equivalent FLOPs; the bf16x3 scheme issues 3 tensor-core MACs per "
+                             "algorithmic MAC, so tensor-pipe busy fraction is ~3x frac",
+                     "traffic": None},
+        "clocks": clocks,
+        "final_loss": losses[-1] if losses else None,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(sample_images=2)
+    print(json.dumps(out), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ CPU arm (oracle port)
+def oracle_step_time(B, reps=1, threads=None, warm=1):
+    """Seconds for one oracle (CPU, torch fp32) SGCls training step on a B-image batch of the same
+    per-image shape; returns (seconds_per_step, cores_used)."""
+    import numpy as np
+    import torch
+    from tests.model_utils import make_masks, CLASSES, RELS as RELCLS, KW
+    from oracle import model as OM
+    from dataloaders.synthetic import make_numpy_batch
+    cores = threads or min(len(os.sched_getaffinity(0)), 32)   # >32 torch threads only oversubscribe here
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    orc = OM.RelModel(CLASSES, RELCLS, mode='sgcls', **KW)
+    with torch.no_grad():
+        for mod in orc.modules():
+            if isinstance(mod, torch.nn.Conv2d):
+                torch.nn.init.kaiming_normal_(mod.weight, nonlinearity='relu')
+        orc.freq_bias.obj_baseline.weight.normal_(0, 1)
+    for p in orc.detector.parameters():
+        p.requires_grad = False
+    orc.train()
+    opt = torch.optim.SGD([p for p in orc.parameters() if p.requires_grad], lr=1e-3, momentum=0.9, weight_decay=1e-4)
+    F = torch.nn.functional
+    times = []
+    for r in range(reps + warm):
+        nb = make_numpy_batch(B, seed=r, boxes_per_img=BOXES, rels_per_img=RELS)
+        n_obj, n_rel = B * BOXES, min(B * BOXES * (BOXES - 1), 256 * B)
+        det, top, ctx = make_masks(n_obj, n_rel, B, seed=r)
+        orc.detector.masks, orc.masks, orc.context.masks = det, top, ctx
+        orc.detector.rng = np.random.RandomState(r)
+        t0 = time.perf_counter()
+        res = orc(torch.from_numpy(nb["imgs"]), nb["im_sizes"], 0, torch.from_numpy(nb["gt_boxes"]),
+                  torch.from_numpy(nb["gt_classes"]), torch.from_numpy(nb["gt_rels"]))
+        loss = F.cross_entropy(res.rm_obj_dists, res.rm_obj_labels) + F.cross_entropy(res.rel_dists, res.rel_labels[:, -1])
+        opt.zero_grad()
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_([p for p in orc.parameters() if p.requires_grad], 5.0)
+        opt.step()
+        if r >= warm:                   # first pass(es) warm the allocator / oneDNN primitives
+            times.append(time.perf_counter() - t0)
+    return sum(times) / len(times), cores
+
+
+def cpu_baseline(sample_images=2):
+    sec, cores = oracle_step_time(sample_images, reps=1)
+    return {"value": sample_images / sec, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "1 timed SGCls train step (after 1 untimed) of the oracle port on a %d-image batch of the same "
+                      "per-image shape (20 boxes, 256 rel triples / image); the reference has no CPU path and "
+                      "PyTorch 0.3 is not installable here (SURVEY.md section 8c)" % sample_images,
+            "seconds_per_step": sec}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    B = 1
+    W = max(args.warmup, 1)
+    # each "step" is a bounded sample: one oracle training step on a 1-image batch
+    import torch
+    sec, cores = oracle_step_time(B, reps=args.steps, warm=W)
+    value = B / sec
+    out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": W, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f32", "data": "synthetic",
+           "config": {"workload": "MotifNet SGCls train_rels.py step, VGG16 backbone, 592x592 synthetic images, 20 GT boxes + "
+                                  "15 GT rels per image; CPU arm steps over a 1-image sample of the per-GPU batch of 6",
+                      "global_batch": B, "parallelism": "cpu"},
+           "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                            "sample": "oracle port (oracle/model.py, torch fp32 CPU, all host threads), 1-image batch per "
+                                      "step; averaged over %d steps after %d warm-up" % (args.steps, W)},
+           "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

@@ -56,6 +56,27 @@ def split_transposed(x):
     return SplitMat(hi, lo, Cc, R, Rp)
 
 
+# Optional per-launch profiling (bench.py's roofline leg): when PROFILE is a list, every tensor-core
+# launch appends (kind, algorithmic_flops, start_event, end_event) recorded on the launching stream.
+PROFILE = None
+
+
+def _prof_begin():
+    if PROFILE is None:
+        return None
+    ev = torch.cuda.Event(enable_timing=True)
+    ev.record()
+    return ev
+
+
+def _prof_end(kind, flops, ev0):
+    if ev0 is None:
+        return
+    ev1 = torch.cuda.Event(enable_timing=True)
+    ev1.record()
+    PROFILE.append((kind, float(flops), ev0, ev1))
+
+
 def gemm(A, B, bias=None, relu=False, want_f32=True, want_split=False):
     """C = A @ B^T (+bias)(relu) with A [M,K], B [N,K] SplitMats. Returns fp32 [M,N] and/or a SplitMat
     of C (pitch round_up(N,64), zero padded) per the flags."""
@@ -72,12 +93,14 @@ def gemm(A, B, bias=None, relu=False, want_f32=True, want_split=False):
     lib = _c.load()
     ws_n = lib.mb200_gemm_workspace_floats(M, N, A.Kp)
     ws = torch.empty(ws_n, dtype=torch.float32, device=dev) if ws_n > 0 else None
+    ev0 = _prof_begin()
     with torch.cuda.device(dev):
         rc = lib.mb200_gemm_bf16x3(_c.ptr(A.hi), _c.ptr(A.lo), _c.ptr(B.hi), _c.ptr(B.lo), M, N, A.Kp,
                                    _c.ptr(bias), 1 if relu else 0, _c.ptr(C), N,
                                    _c.ptr(Cs.hi) if Cs else None, _c.ptr(Cs.lo) if Cs else None,
                                    Cs.Kp if Cs else 0, _c.ptr(ws), _c.cur_stream())
     _c.check(rc, "mb200_gemm_bf16x3")
+    _prof_end("gemm", 2.0 * M * N * A.K, ev0)
     if want_f32 and want_split:
         return C, Cs
     return C if want_f32 else Cs
@@ -220,11 +243,13 @@ def conv3x3_relu(xs, B, H, W, Cin, conv, want_f32=False, want_split=True):
     y = torch.empty(B, H, W, Cout, dtype=torch.float32, device=dev) if want_f32 else None
     yh = torch.empty(B, H, W, Cout, dtype=torch.bfloat16, device=dev) if want_split else None
     yl = torch.empty_like(yh) if want_split else None
+    ev0 = _prof_begin()
     with torch.cuda.device(dev):
         rc = _c.load().mb200_conv3x3_bf16x3(_c.ptr(xs[0]), _c.ptr(xs[1]), _c.ptr(wsp.hi), _c.ptr(wsp.lo), B, H, W, Cin,
                                             Cout, _c.ptr(conv.bias.detach()) if conv.bias is not None else None, 1,
                                             _c.ptr(y), _c.ptr(yh), _c.ptr(yl), _c.cur_stream())
     _c.check(rc, "mb200_conv3x3_bf16x3")
+    _prof_end("conv3x3", 2.0 * B * H * W * Cout * 9 * Cin, ev0)
     return y, ((yh, yl) if want_split else None)
 
 

@@ -81,8 +81,13 @@ def last_error():
     return load().mb200_last_error().decode()
 
 
+LAUNCHER_CALLS = 0   # successful C-ABI launcher calls (each launches >= 1 kernel of this library)
+
+
 def check(rc, what):
     """The launchers return 1 on success (reference convention); anything else raises."""
+    global LAUNCHER_CALLS
+    LAUNCHER_CALLS += 1
     if rc != 1:
         raise MotifsB200Error("%s failed (code %d): %s" % (what, rc, last_error()))
 

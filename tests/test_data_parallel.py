@@ -1,0 +1,45 @@
+"""CPU (gloo, world_size 2): the gradient all-reduce used for the N>1 path averages bucketed gradients
+and leaves every rank with identical values — host logic of lib/data_parallel.py."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "neural-motifs_b200"))
+    from lib.data_parallel import init_from_env, GradAllReducer
+    r, w, _ = init_from_env("gloo")
+    assert (r, w) == (rank, world)
+    torch.manual_seed(0)
+    params = [torch.nn.Parameter(torch.zeros(n)) for n in (5, 300, 7, 1024)]
+    frozen = torch.nn.Parameter(torch.zeros(3), requires_grad=False)
+    for i, p in enumerate(params):
+        p.grad = torch.full_like(p, float(rank + 1) * (i + 1))
+    params[2].grad = None if rank == 1 else params[2].grad          # a rank without a grad contributes zeros
+    red = GradAllReducer(params + [frozen], bucket_bytes=2048)     # forces several buckets
+    assert len(red.buckets) >= 2
+    red.all_reduce()
+    out[rank] = [p.grad.clone() for p in params]
+    dist.destroy_process_group()
+
+
+def test_grad_all_reduce_gloo_world2():
+    mgr = mp.Manager()
+    out = mgr.dict()
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
+    g0, g1 = out[0], out[1]
+    for i, (a, b) in enumerate(zip(g0, g1)):
+        assert torch.equal(a, b)
+        expect = (1 + 2) / 2 * (i + 1) if i != 2 else 1 * (i + 1) / 2
+        assert torch.allclose(a, torch.full_like(a, expect))
