@@ -123,25 +123,24 @@ def build_model(device, seed=0):
 
 
 def get_optim(model, lr):
-    """models/train_rels.py:57-70 (SGD branch): fc layers of roi_fmap* at lr/10, momentum 0.9, l2 1e-4."""
-    import torch
+    """models/train_rels.py:57-70 (SGD branch: fc layers of roi_fmap* at lr/10, momentum 0.9, l2 1e-4) and
+    :145-150 (clip 5) as the fused flat-buffer optimizer (lib/fused_optim.py, csrc/optim.cu)."""
+    from lib.fused_optim import FlatSGD
     fc = [p for n, p in model.named_parameters() if n.startswith('roi_fmap') and p.requires_grad]
     non_fc = [p for n, p in model.named_parameters() if not n.startswith('roi_fmap') and p.requires_grad]
-    return torch.optim.SGD([{'params': fc, 'lr': lr / 10.0}, {'params': non_fc}], weight_decay=1e-4, lr=lr, momentum=0.9)
+    return FlatSGD([(fc, lr / 10.0), (non_fc, lr)], momentum=0.9, weight_decay=1e-4, max_norm=5.0)
 
 
-def train_step(model, optimizer, reducer, fwd_tuple=None, blob=None):
-    """models/train_rels.py:118-152 (train_batch): forward, two cross-entropies, backward, clip 5, step."""
-    import torch
+def train_step(model, optimizer, reducer=None, fwd_tuple=None, blob=None):
+    """models/train_rels.py:118-152 (train_batch): forward, two cross-entropies, backward, clip 5, step.
+    The data-parallel gradient average is one all-reduce per flat gradient buffer."""
     from torch.nn import functional as F
-    from lib.pytorch_misc import clip_grad_norm
     result = model[blob] if blob is not None else model(*fwd_tuple)
     loss = F.cross_entropy(result.rm_obj_dists, result.rm_obj_labels) + \
         F.cross_entropy(result.rel_dists, result.rel_labels[:, -1])
-    optimizer.zero_grad(set_to_none=True)
+    optimizer.zero_grad()
     loss.backward()
-    reducer.all_reduce()
-    clip_grad_norm([(n, p) for n, p in model.named_parameters() if p.grad is not None], max_norm=5.0, clip=True)
+    optimizer.all_reduce_grads()
     optimizer.step()
     return loss
 
@@ -152,7 +151,7 @@ def run_b200(args):
     import torch.distributed as dist
     import motifs_cabi
     from lib import tc_ops
-    from lib.data_parallel import init_from_env, GradAllReducer
+    from lib.data_parallel import init_from_env
     from dataloaders.synthetic import make_numpy_batch, SyntheticBlob
 
     rank, world, local = init_from_env("nccl")
@@ -163,7 +162,7 @@ def run_b200(args):
     motifs_cabi.load()
     model = build_model(dev, seed=0)
     opt = get_optim(model, lr=1e-3 * BATCH_PER_GPU)      # train_rels.py:193: lr * num_gpus * batch_size
-    reducer = GradAllReducer(model.parameters())
+    reducer = None
     pool = [make_numpy_batch(BATCH_PER_GPU, seed=100 * rank + i, boxes_per_img=BOXES, rels_per_img=RELS,
                              image_offset=0) for i in range(4)]
     blobs = [SyntheticBlob(nb, dev) for nb in pool]
@@ -331,6 +330,10 @@ def run_reference(args):
 
 
 if __name__ == "__main__":
+    import faulthandler
+    wd = int(os.environ.get("MOTIFS_WATCHDOG_S", "0"))
+    if wd > 0:      # dump every thread's Python stack and exit if the run wedges (debugging aid)
+        faulthandler.dump_traceback_later(wd, exit=True)
     a = parse()
     if a.impl == "reference":
         run_reference(a)

@@ -159,6 +159,13 @@ int mb200_stem_weight_split(const float* w_oihw, int O, void* hi, void* lo, cuda
 int mb200_maxpool2_nhwc_split(const void* xhi, const void* xlo, int B, int H, int W, int C, void* yhi, void* ylo,
                               cudaStream_t stream);
 
+/* Fused clip + weight-decay + momentum SGD over a flat fp32 buffer (replaces the caller-side
+ * clip_grad_norm + optim.SGD.step of models/train_rels.py:145-150). total_norm_dev: device scalar with
+ * the global gradient norm, or NULL for no clipping. Pointers 16-byte aligned. */
+int mb200_sgd_momentum_clip(float* params, float* grads, float* momentum_buf, long long n, float lr, float momentum,
+                            float weight_decay, const float* total_norm_dev, float max_norm, int first_step,
+                            int zero_grad, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

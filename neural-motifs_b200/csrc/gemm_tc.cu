@@ -16,9 +16,10 @@
 // the NHWC activation (out-of-bounds zero fill = the padding), no im2col buffer.
 //
 // Layout contract: A [M, Kp] and B [N, Kp] bf16, K contiguous ("K-major"), Kp % 64 == 0 with
-// zero padding; C row-major. Tile 128 x BN x 64, 128-byte swizzle, 3-stage ring (64 KB / stage),
-// warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2..5 = epilogue (one TMEM lane
-// quarter each).
+// zero padding; C row-major. Tile 128 x 128 x 64, 128-byte swizzle, 3-stage ring (64 KB / stage).
+// Persistent: one CTA per SM walks a static tile list; warp 0 = TMA producer, warp 1 = MMA issuer +
+// TMEM owner, warps 2..5 = epilogue (one TMEM lane quarter each). Two TMEM accumulators (256
+// columns) let the epilogue of tile i run under the MMAs of tile i+1.
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -26,11 +27,12 @@ namespace {
 
 constexpr int BM = 128, BN = 128, BK = 64;
 constexpr int STAGES = 3;
+constexpr int ACC_STAGES = 2;                  // TMEM accumulators: epilogue of tile i overlaps the MMAs of tile i+1
 constexpr int TILE_A = BM * BK * 2;            // 16 KB
 constexpr int TILE_B = BN * BK * 2;            // 16 KB
 constexpr int STAGE_BYTES = 2 * TILE_A + 2 * TILE_B;
 constexpr int kGemmThreads = 192;
-constexpr int TMEM_COLS = 128;
+constexpr int TMEM_COLS = ACC_STAGES * BN;     // 256 columns
 constexpr int TH = 8, TW = 16;                 // conv: spatial tile = 128 output pixels
 constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 
@@ -38,6 +40,7 @@ struct Params {
   int M, N;                  // logical output size (conv: M = B*H*W pixels, N = Cout)
   int kblocks;               // k-blocks per split
   int splits;
+  int m_tiles, n_tiles;      // tile grid (conv: m_tiles = images * tiles_h * tiles_w)
   // epilogue targets (any may be null)
   float* C; long long ldc;
   __nv_bfloat16* Chi; __nv_bfloat16* Clo; long long ldsplit;
@@ -47,6 +50,33 @@ struct Params {
   int conv; int H, W, Cin, tiles_w, tiles_h;
 };
 
+struct TileCoord { int split, m0, n0, img, h0, w0; };
+
+__device__ __forceinline__ TileCoord decode_tile(const Params& p, int t) {
+  TileCoord tc_;
+  const int per_split = p.m_tiles * p.n_tiles;
+  tc_.split = t / per_split;
+  const int r = t - tc_.split * per_split;
+  const int mi = r / p.n_tiles;                 // n-tiles fastest: neighbouring CTAs share the A tile in L2
+  tc_.n0 = (r - mi * p.n_tiles) * BN;
+  tc_.m0 = mi * BM; tc_.img = 0; tc_.h0 = 0; tc_.w0 = 0;
+  if (p.conv) {
+    const int per_img = p.tiles_w * p.tiles_h;
+    tc_.img = mi / per_img;
+    const int q = mi - tc_.img * per_img;
+    const int th = q / p.tiles_w;
+    tc_.h0 = th * TH;
+    tc_.w0 = (q - th * p.tiles_w) * TW;
+  }
+  return tc_;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// Persistent: grid = min(#tiles, #SMs); every role loops over the same static tile sequence.
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant__ CUtensorMap tmAlo,
                    const __grid_constant__ CUtensorMap tmBhi, const __grid_constant__ CUtensorMap tmBlo,
@@ -55,30 +85,17 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_const
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = (uint64_t*)(smem + (size_t)STAGES * STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full_bar = empty_bar + STAGES;
-  uint32_t* tmem_slot = (uint32_t*)(tmem_full_bar + 1);
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + ACC_STAGES;
+  uint32_t* tmem_slot = (uint32_t*)(tempty_bar + ACC_STAGES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * BN;
-  const int split = blockIdx.z;
-  const int kb0 = split * p.kblocks;
-
-  // tile origin
-  int m0 = 0, img = 0, h0 = 0, w0 = 0;
-  if (!p.conv) {
-    m0 = blockIdx.y * BM;
-  } else {
-    const int per_img = p.tiles_w * p.tiles_h;
-    img = blockIdx.y / per_img;
-    const int t = blockIdx.y - img * per_img;
-    h0 = (t / p.tiles_w) * TH;
-    w0 = (t - (t / p.tiles_w) * p.tiles_w) * TW;
-  }
+  const int total_tiles = p.splits * p.m_tiles * p.n_tiles;
 
   if (warp == 0 && lane == 0) {
     tc::prefetch_tmap(&tmAhi); tc::prefetch_tmap(&tmAlo); tc::prefetch_tmap(&tmBhi); tc::prefetch_tmap(&tmBlo);
     for (int s = 0; s < STAGES; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
-    tc::mbar_init(tmem_full_bar, 1);
+    for (int s = 0; s < ACC_STAGES; ++s) { tc::mbar_init(&tfull_bar[s], 1); tc::mbar_init(&tempty_bar[s], 4); }
     tc::fence_barrier_init();
   }
   if (warp == 1) tc::tmem_alloc(tmem_slot, TMEM_COLS);
@@ -92,23 +109,27 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_const
       // ---------------------------------------------------------------- TMA producer
       int stage = 0; uint32_t phase = 0;
       const int cblocks = p.conv ? p.Cin / BK : 0;
-      for (int kb = 0; kb < p.kblocks; ++kb) {
-        tc::mbar_wait(&empty_bar[stage], phase ^ 1);
-        uint8_t* st = smem + (size_t)stage * STAGE_BYTES;
-        tc::mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
-        const int kg = kb0 + kb;
-        if (!p.conv) {
-          tc::tma_load_2d(st, &tmAhi, &full_bar[stage], kg * BK, m0);
-          tc::tma_load_2d(st + TILE_A, &tmAlo, &full_bar[stage], kg * BK, m0);
-        } else {
-          const int tap = kg / cblocks, cb = kg - tap * cblocks;
-          const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
-          tc::tma_load_4d(st, &tmAhi, &full_bar[stage], cb * BK, w0 + dx, h0 + dy, img);
-          tc::tma_load_4d(st + TILE_A, &tmAlo, &full_bar[stage], cb * BK, w0 + dx, h0 + dy, img);
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const TileCoord tl = decode_tile(p, t);
+        const int kb0 = tl.split * p.kblocks;
+        for (int kb = 0; kb < p.kblocks; ++kb) {
+          tc::mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* st = smem + (size_t)stage * STAGE_BYTES;
+          tc::mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+          const int kg = kb0 + kb;
+          if (!p.conv) {
+            tc::tma_load_2d(st, &tmAhi, &full_bar[stage], kg * BK, tl.m0);
+            tc::tma_load_2d(st + TILE_A, &tmAlo, &full_bar[stage], kg * BK, tl.m0);
+          } else {
+            const int tap = kg / cblocks, cb = kg - tap * cblocks;
+            const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
+            tc::tma_load_4d(st, &tmAhi, &full_bar[stage], cb * BK, tl.w0 + dx, tl.h0 + dy, tl.img);
+            tc::tma_load_4d(st + TILE_A, &tmAlo, &full_bar[stage], cb * BK, tl.w0 + dx, tl.h0 + dy, tl.img);
+          }
+          tc::tma_load_2d(st + 2 * TILE_A, &tmBhi, &full_bar[stage], kg * BK, tl.n0);
+          tc::tma_load_2d(st + 2 * TILE_A + TILE_B, &tmBlo, &full_bar[stage], kg * BK, tl.n0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        tc::tma_load_2d(st + 2 * TILE_A, &tmBhi, &full_bar[stage], kg * BK, n0);
-        tc::tma_load_2d(st + 2 * TILE_A + TILE_B, &tmBlo, &full_bar[stage], kg * BK, n0);
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
     __syncwarp();
@@ -117,22 +138,30 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_const
       // ---------------------------------------------------------------- MMA issuer
       constexpr uint32_t idesc = tc::umma_idesc_bf16_f32(BM, BN);
       int stage = 0; uint32_t phase = 0;
-      for (int kb = 0; kb < p.kblocks; ++kb) {
-        tc::mbar_wait(&full_bar[stage], phase);
+      int it = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        tc::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);      // epilogue has drained this accumulator
         tc::tc_fence_after();
-        const uint32_t sa = tc::smem_u32(smem + (size_t)stage * STAGE_BYTES);
-        const uint64_t a_hi = tc::umma_desc_k_sw128(sa), a_lo = tc::umma_desc_k_sw128(sa + TILE_A);
-        const uint64_t b_hi = tc::umma_desc_k_sw128(sa + 2 * TILE_A), b_lo = tc::umma_desc_k_sw128(sa + 2 * TILE_A + TILE_B);
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < p.kblocks; ++kb) {
+          tc::mbar_wait(&full_bar[stage], phase);
+          tc::tc_fence_after();
+          const uint32_t sa = tc::smem_u32(smem + (size_t)stage * STAGE_BYTES);
+          const uint64_t a_hi = tc::umma_desc_k_sw128(sa), a_lo = tc::umma_desc_k_sw128(sa + TILE_A);
+          const uint64_t b_hi = tc::umma_desc_k_sw128(sa + 2 * TILE_A), b_lo = tc::umma_desc_k_sw128(sa + 2 * TILE_A + TILE_B);
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k) {
-          const uint64_t adv = (uint64_t)((k * 16 * 2) >> 4);   // 32 bytes per 16-wide k step
-          tc::umma_bf16(tmem_base, a_hi + adv, b_hi + adv, idesc, (kb | k) != 0);
-          tc::umma_bf16(tmem_base, a_hi + adv, b_lo + adv, idesc, 1);
-          tc::umma_bf16(tmem_base, a_lo + adv, b_hi + adv, idesc, 1);
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t adv = (uint64_t)((k * 16 * 2) >> 4);   // 32 bytes per 16-wide k step
+            tc::umma_bf16(tmem_d, a_hi + adv, b_hi + adv, idesc, (kb | k) != 0);
+            tc::umma_bf16(tmem_d, a_hi + adv, b_lo + adv, idesc, 1);
+            tc::umma_bf16(tmem_d, a_lo + adv, b_hi + adv, idesc, 1);
+          }
+          tc::umma_commit(&empty_bar[stage]);          // frees the smem slot when these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        tc::umma_commit(&empty_bar[stage]);          // frees the smem slot when these MMAs retire
-        if (kb == p.kblocks - 1) tc::umma_commit(tmem_full_bar);
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        tc::umma_commit(&tfull_bar[acc]);              // accumulator complete -> epilogue
       }
     }
     __syncwarp();
@@ -140,62 +169,90 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_const
     // ------------------------------------------------------------------ epilogue (warps 2..5)
     const int q = warp & 3;                    // TMEM lane quarter this warp may access
     const int r = q * 32 + lane;               // tile row == TMEM lane
-    tc::mbar_wait(tmem_full_bar, 0);
-    tc::tc_fence_after();
-    long long row;                             // output row index (M axis), or -1 when masked
-    if (!p.conv) {
-      row = (m0 + r < p.M) ? (long long)(m0 + r) : -1;
-    } else {
-      const int h = h0 + r / TW, w = w0 + (r % TW);
-      row = (h < p.H && w < p.W) ? ((long long)img * p.H + h) * p.W + w : -1;
-    }
+    int it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      const TileCoord tl = decode_tile(p, t);
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      tc::mbar_wait(&tfull_bar[acc], acc_phase);
+      tc::tc_fence_after();
+      long long row;                             // output row index (M axis), or -1 when masked
+      if (!p.conv) {
+        row = (tl.m0 + r < p.M) ? (long long)(tl.m0 + r) : -1;
+      } else {
+        const int h = tl.h0 + r / TW, w = tl.w0 + (r % TW);
+        row = (h < p.H && w < p.W) ? ((long long)tl.img * p.H + h) * p.W + w : -1;
+      }
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      __syncwarp();                            // tcgen05.ld is warp-collective: reconverge first
-      uint32_t v[32];
-      tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
-      tc::tmem_ld_wait();
-      const int nb = n0 + c * 32;
-      if (row < 0 || nb >= p.N) continue;
-      const int ncols = min(32, p.N - nb);
-      if (p.splits > 1) {
-        float* dst = p.partial + ((size_t)split * p.M + row) * p.N + nb;
-        for (int j = 0; j < ncols; ++j) dst[j] = __uint_as_float(v[j]);
-        continue;
-      }
-      float x[32];
+      for (int c = 0; c < BN / 32; ++c) {
+        __syncwarp();                            // tcgen05.ld is warp-collective: reconverge first
+        uint32_t v[32];
+        tc::tmem_ld_32x32(taddr + (uint32_t)(c * 32), v);
+        tc::tmem_ld_wait();
+        const int nb = tl.n0 + c * 32;
+        if (row < 0 || nb >= p.N) continue;
+        const int ncols = min(32, p.N - nb);
+        if (p.splits > 1) {
+          float* dst = p.partial + ((size_t)tl.split * p.M + row) * p.N + nb;
+          if (ncols == 32 && ((((uintptr_t)dst) & 15) == 0)) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float t = __uint_as_float(v[j]);
-        if (p.bias && j < ncols) t += __ldg(p.bias + nb + j);
-        if (p.relu) t = fmaxf(t, 0.f);
-        x[j] = t;
-      }
-      if (p.C) {
-        float* dst = p.C + row * p.ldc + nb;
-        if (ncols == 32 && ((((uintptr_t)dst) & 15) == 0)) {
+            for (int j = 0; j < 8; ++j) ((uint4*)dst)[j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          } else {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) ((float4*)dst)[j] = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
-        } else {
-          for (int j = 0; j < ncols; ++j) dst[j] = x[j];
+            for (int j = 0; j < 32; ++j) if (j < ncols) dst[j] = __uint_as_float(v[j]);
+          }
+          continue;
+        }
+        float x[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float tt = __uint_as_float(v[j]);
+          if (p.bias && j < ncols) tt += __ldg(p.bias + nb + j);
+          if (p.relu) tt = fmaxf(tt, 0.f);
+          x[j] = tt;
+        }
+        if (p.C) {
+          float* dst = p.C + row * p.ldc + nb;
+          if (ncols == 32 && ((((uintptr_t)dst) & 15) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) ((float4*)dst)[j] = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (j < ncols) dst[j] = x[j];
+          }
+        }
+        if (p.Chi) {
+          uint32_t hi[16], lo[16];             // packed bf16 pairs, registers only
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float a0 = x[2 * j], a1 = x[2 * j + 1];
+            const __nv_bfloat16 h0 = __float2bfloat16_rn(a0), h1 = __float2bfloat16_rn(a1);
+            hi[j] = pack_bf16x2(a0, a1);
+            lo[j] = pack_bf16x2(a0 - __bfloat162float(h0), a1 - __bfloat162float(h1));
+          }
+          __nv_bfloat16* dh = p.Chi + row * p.ldsplit + nb;
+          __nv_bfloat16* dl = p.Clo + row * p.ldsplit + nb;
+          if (ncols == 32 && ((((uintptr_t)dh) & 15) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              ((uint4*)dh)[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+              ((uint4*)dl)[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (j < ncols) {
+              __nv_bfloat16 h, l; tc::split_bf16(x[j], h, l);
+              dh[j] = h; dl[j] = l;
+            }
+          }
         }
       }
-      if (p.Chi) {
-        __align__(16) __nv_bfloat16 hi[32];
-        __align__(16) __nv_bfloat16 lo[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) tc::split_bf16(x[j], hi[j], lo[j]);
-        __nv_bfloat16* dh = p.Chi + row * p.ldsplit + nb;
-        __nv_bfloat16* dl = p.Clo + row * p.ldsplit + nb;
-        if (ncols == 32 && ((((uintptr_t)dh) & 15) == 0)) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) { ((uint4*)dh)[j] = ((const uint4*)hi)[j]; ((uint4*)dl)[j] = ((const uint4*)lo)[j]; }
-        } else {
-          for (int j = 0; j < ncols; ++j) { dh[j] = hi[j]; dl[j] = lo[j]; }
-        }
-      }
+      // accumulator drained: hand it back to the MMA warp (4 arrivals, one per epilogue warp)
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&tempty_bar[acc]);
     }
-    tc::tc_fence_before();
   }
   __syncthreads();
   if (warp == 1) { tc::tc_fence_after(); tc::tmem_dealloc(tmem_base, TMEM_COLS); }
@@ -269,9 +326,12 @@ int ensure_attr() {
 }
 
 int launch(const CUtensorMap& ahi, const CUtensorMap& alo, const CUtensorMap& bhi, const CUtensorMap& blo,
-           const Params& p, dim3 grid, cudaStream_t stream) {
+           const Params& p, cudaStream_t stream) {
   int rc = ensure_attr();
   if (rc != MB200_OK) return rc;
+  const long long tiles = (long long)p.splits * p.m_tiles * p.n_tiles;
+  if (tiles > 0x7fffffffLL) return MB200_ERR_UNSUPPORTED;
+  const int grid = (int)min(tiles, (long long)kNumSMs);      // persistent: one CTA per SM
   gemm_bf16x3_kernel<<<grid, kGemmThreads, SMEM_BYTES, stream>>>(ahi, alo, bhi, blo, p);
   MB200_CHECK_LAUNCH("gemm_bf16x3_kernel");
   if (p.splits > 1) {
@@ -324,9 +384,8 @@ int mb200_gemm_bf16x3(const void* Ahi, const void* Alo, const void* Bhi, const v
   p.kblocks = kblocks / p.splits;
   p.C = C; p.ldc = ldc; p.Chi = (__nv_bfloat16*)Chi; p.Clo = (__nv_bfloat16*)Clo; p.ldsplit = ldsplit;
   p.bias = bias; p.relu = relu; p.partial = workspace; p.conv = 0;
-  dim3 grid(mb200_div_up(N, BN), mb200_div_up(M, BM), p.splits);
-  if (grid.y > 65535) return MB200_ERR_UNSUPPORTED;
-  return launch(ta, tal, tb, tbl, p, grid, stream);
+  p.m_tiles = mb200_div_up(M, BM); p.n_tiles = mb200_div_up(N, BN);
+  return launch(ta, tal, tb, tbl, p, stream);
 }
 
 // 3x3 / stride 1 / pad 1 convolution as implicit GEMM. x: NHWC bf16 pair [B,H,W,Cin] (Cin % 64 == 0);
@@ -348,13 +407,8 @@ int mb200_conv3x3_bf16x3(const void* xhi, const void* xlo, const void* whi, cons
   p.C = y; p.ldc = Cout; p.Chi = (__nv_bfloat16*)yhi; p.Clo = (__nv_bfloat16*)ylo; p.ldsplit = Cout;
   p.bias = bias; p.relu = relu; p.partial = nullptr;
   p.conv = 1; p.H = H; p.W = W; p.Cin = Cin; p.tiles_w = mb200_div_up(W, TW); p.tiles_h = mb200_div_up(H, TH);
-  const long long tiles = (long long)B * p.tiles_w * p.tiles_h;
-  if (tiles > 65535) {
-    // grid.y limit: fold tiles into x (n-tiles stay fastest so that B tiles of a pixel tile share A in L2)
-    return MB200_ERR_UNSUPPORTED;
-  }
-  dim3 grid(mb200_div_up(Cout, BN), (unsigned)tiles, 1);
-  return launch(ta, tal, tb, tbl, p, grid, stream);
+  p.m_tiles = B * p.tiles_w * p.tiles_h; p.n_tiles = mb200_div_up(Cout, BN);
+  return launch(ta, tal, tb, tbl, p, stream);
 }
 
 }  // extern "C"

@@ -87,17 +87,23 @@ __device__ __forceinline__ void build_tables(const float* __restrict__ boxes, in
 }
 
 // ---------------------------------------------------------------- forward, NCHW -> [N,C,PH,PW]
-constexpr int kLanes = 32;               // channels per pass == warp width
-constexpr int kPasses = 2;               // passes per CTA -> 64 channels per CTA
-constexpr int kWinStride = kLanes + 1;   // [pixel][channel] rows padded to 33 words
-constexpr int kStageMaxArea = 256;       // windows up to 16x16 px are staged
+// v4 (ncu on v3: issue slots 70 % busy, 108 thread-instructions per output -> instruction bound):
+// one CTA per (roi, 64-channel chunk); the window of all 64 planes is staged ONCE, transposed to
+// [pixel][channel] with an odd row stride (65 words) so that
+//   * staging stores (lanes = consecutive window pixels of one plane) are conflict-free,
+//   * compute loads (lanes = channels c and c+32 of ONE bin) are conflict-free and the bin's
+//     descriptor is a broadcast read amortised over 2 outputs per lane,
+//   * results go to a [channel][bin] tile (stride bins, odd for 7x7) and leave as one contiguous
+//     run of 16-byte vector stores.
+constexpr int kChunkN = 64;               // channels per CTA
+constexpr int kWinStride = kChunkN + 1;   // 65 words
+constexpr int kStageMaxArea = 196;        // windows up to 14x14 px are staged (boxes up to ~200 px)
 
-struct __align__(16) BinDesc { int o00, o01, o10, o11; };   // window pixel indices of the 4 corners
+struct __align__(16) BinDesc { int o00, o01, o10, o11; };   // window offsets (pixel * kWinStride) or plane offsets
 struct __align__(8) BinW { float wx, wy; };
-
-// Warp 0 builds the axis tables and the window; everyone then derives bin descriptors.
 struct RoiHead { int b_in, y_lo, x_lo, wh, ww, any_ok, bad_batch; };
 
+// Warp 0 builds the axis tables and the window.
 __device__ __forceinline__ void roi_preamble(const float* __restrict__ boxes, int n, int batch, int H, int W,
                                              int PH, int PW, AxisTab& ty, AxisTab& tx, RoiHead& hd) {
   if (threadIdx.x < 32) {
@@ -130,130 +136,107 @@ __device__ __forceinline__ void roi_preamble(const float* __restrict__ boxes, in
   __syncthreads();
 }
 
+// v5 (ncu on v3/v4: issue-bound, ~50-100 thread-instructions per output, most of them in the
+// register-staged window copy and in shared-memory table reads): the window is copied with
+// cp.async (one instruction per element, no register round trip) into [channel][pixel]; in the
+// compute phase a lane IS a bin — its 4 window offsets and 2 weights live in registers for the whole
+// CTA — and loops over channels: 4 LDS + 3 FMA + 1 coalesced STG per output, no output tile.
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+
 __global__ void __launch_bounds__(kThreads)
 roi_align_fwd_nchw_kernel(const float* __restrict__ feat, const float* __restrict__ boxes,
                           int num_boxes, int batch, int H, int W, int PH, int PW, int C,
                           float extrap, float* __restrict__ out) {
-  extern __shared__ __align__(16) float dsm[];
+  extern __shared__ __align__(16) float s_win[];   // [64][area]
   __shared__ AxisTab ty, tx;
   __shared__ RoiHead hd;
-  __shared__ BinDesc s_desc[kMaxBins];
-  __shared__ BinW s_w[kMaxBins];
-  __shared__ int s_ok[kMaxBins];
   __shared__ int s_goff[kStageMaxArea];
   const int bins = PH * PW;
-  float* s_out = dsm;                        // [32][bins]
-  float* s_win = dsm + kLanes * bins;        // [area][33]
-
   const int n = blockIdx.x;
-  const int cbase = blockIdx.y * (kLanes * kPasses);
+  const int c0 = blockIdx.y * kChunkN;
+  const int nc = min(kChunkN, C - c0);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int kWarps = kThreads / 32;
 
   roi_preamble(boxes, n, batch, H, W, PH, PW, ty, tx, hd);
 
-  const int nc_cta = min(kLanes * kPasses, C - cbase);
-  float* o_cta = out + ((size_t)n * C + cbase) * bins;
+  float* o = out + ((size_t)n * C + c0) * bins;
+  const int total = nc * bins;
   if (!hd.any_ok) {
     const float v = hd.bad_batch ? 0.f : extrap;
-    for (int i = tid; i < nc_cta * bins; i += kThreads) o_cta[i] = v;
+    for (int i = tid; i < total; i += kThreads) o[i] = v;
     return;
   }
   const int area = hd.wh * hd.ww;
   const bool staged = area <= kStageMaxArea;
   const int ww = hd.ww;
-  for (int b = tid; b < bins; b += kThreads) {
-    const int y = b / PW, x = b - y * PW;
-    const int ok = ty.ok[y] & tx.ok[x];
-    s_ok[b] = ok;
-    BinW w; w.wx = tx.lerp[x]; w.wy = ty.lerp[y]; s_w[b] = w;
-    BinDesc d;
-    if (staged) {
-      const int yt = ty.lo[y] - hd.y_lo, yb = ty.hi[y] - hd.y_lo;
-      const int xl = tx.lo[x] - hd.x_lo, xr = tx.hi[x] - hd.x_lo;
-      d.o00 = ok ? (yt * ww + xl) * kWinStride : 0; d.o01 = ok ? (yt * ww + xr) * kWinStride : 0;
-      d.o10 = ok ? (yb * ww + xl) * kWinStride : 0; d.o11 = ok ? (yb * ww + xr) * kWinStride : 0;
-    } else {
-      d.o00 = ty.lo[y] * W + tx.lo[x]; d.o01 = ty.lo[y] * W + tx.hi[x];
-      d.o10 = ty.hi[y] * W + tx.lo[x]; d.o11 = ty.hi[y] * W + tx.hi[x];
-    }
-    s_desc[b] = d;
-  }
-  if (staged)
-    for (int r = tid; r < area; r += kThreads) {
-      const int wy_ = r / ww, wx_ = r - wy_ * ww;
-      s_goff[r] = (hd.y_lo + wy_) * W + hd.x_lo + wx_;
-    }
-  __syncthreads();
-
   const size_t HW = (size_t)H * W;
-  const bool vec_ok = (((size_t)C * bins) % 4 == 0) && ((((uintptr_t)out) & 15) == 0) && ((kLanes * bins) % 4 == 0);
-  for (int pass = 0; pass < kPasses; ++pass) {
-    const int c0 = cbase + pass * kLanes;
-    const int nc = min(kLanes, C - c0);
-    if (nc <= 0) break;
-    const float* plane0 = feat + ((size_t)hd.b_in * C + c0) * HW;
-    float* o = out + ((size_t)n * C + c0) * bins;
-    if (staged) {
-      // stage: warp -> 4 channels, lanes -> window pixels; all loads of a batch are issued before
-      // any shared-memory store so ~16 L2 requests per thread are in flight (the loop is
-      // latency-bound otherwise). Transposed store, row stride 33: conflict-free.
-      for (int rb = 0; rb < area; rb += 128) {
-        int goff[4]; bool live[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int r = rb + j * 32 + lane;
-          live[j] = r < area;
-          goff[j] = live[j] ? s_goff[r] : 0;
-        }
-        float v[4][4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int c = warp + i * kWarps;
-          const float* p = plane0 + (size_t)min(c, nc - 1) * HW;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) v[i][j] = live[j] ? __ldg(p + goff[j]) : 0.f;
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int c = warp + i * kWarps;
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            if (live[j] && c < nc) s_win[(rb + j * 32 + lane) * kWinStride + c] = v[i][j];
-        }
-      }
-      __syncthreads();
-      // compute: warp -> bin, lanes -> channels
-      const float* wl = s_win + lane;
-      for (int b = warp; b < bins; b += kWarps) {
-        const BinDesc d = s_desc[b];
-        const BinW w = s_w[b];
-        float v = extrap;
-        if (s_ok[b]) v = bilerp(wl[d.o00], wl[d.o01], wl[d.o10], wl[d.o11], w.wx, w.wy);
-        s_out[lane * bins + b] = v;
-      }
-      __syncthreads();
-      // store: the chunk's output is one contiguous run of nc*bins floats
-      const int total = nc * bins;
-      if (vec_ok) {
-        const float4* src = (const float4*)s_out;
-        float4* dst = (float4*)o;
-        for (int i = tid; i < total / 4; i += kThreads) dst[i] = src[i];
+  const float* plane0 = feat + ((size_t)hd.b_in * C + c0) * HW;
+
+  // bin slot of this thread: slots = bins rounded up to a warp multiple, groups = 256 / slots
+  const int slots = (bins + 31) & ~31;
+  const int groups = kThreads / slots;           // >= 1 because bins <= 256
+  const int grp = tid / slots, b = tid - grp * slots;
+  const bool has_bin = (grp < groups) && (b < bins);
+  int o00 = 0, o01 = 0, o10 = 0, o11 = 0, okb = 0;
+  float wx = 0.f, wy = 0.f;
+  if (has_bin) {
+    const int y = b / PW, x = b - y * PW;
+    okb = ty.ok[y] & tx.ok[x];
+    wx = tx.lerp[x]; wy = ty.lerp[y];
+    if (okb) {
+      if (staged) {
+        const int yt = ty.lo[y] - hd.y_lo, yb = ty.hi[y] - hd.y_lo;
+        const int xl = tx.lo[x] - hd.x_lo, xr = tx.hi[x] - hd.x_lo;
+        o00 = yt * ww + xl; o01 = yt * ww + xr; o10 = yb * ww + xl; o11 = yb * ww + xr;
       } else {
-        for (int i = tid; i < total; i += kThreads) o[i] = s_out[i];
+        o00 = ty.lo[y] * W + tx.lo[x]; o01 = ty.lo[y] * W + tx.hi[x];
+        o10 = ty.hi[y] * W + tx.lo[x]; o11 = ty.hi[y] * W + tx.hi[x];
       }
-      __syncthreads();
-    } else {
-      const int total = nc * bins;
-      for (int i = tid; i < total; i += kThreads) {
-        const int c = i / bins, b = i - c * bins;
+    }
+  }
+  if (!staged) {
+    // large window (bins >= 1 px apart, nothing to re-use): gather straight from global / L1
+    if (has_bin)
+      for (int c = grp; c < nc; c += groups) {
         const float* p = plane0 + (size_t)c * HW;
-        const BinDesc d = s_desc[b];
-        const BinW w = s_w[b];
         float v = extrap;
-        if (s_ok[b]) v = bilerp(__ldg(p + d.o00), __ldg(p + d.o01), __ldg(p + d.o10), __ldg(p + d.o11), w.wx, w.wy);
-        o[i] = v;
+        if (okb) v = bilerp(__ldg(p + o00), __ldg(p + o01), __ldg(p + o10), __ldg(p + o11), wx, wy);
+        o[(size_t)c * bins + b] = v;
       }
+    return;
+  }
+  for (int r = tid; r < area; r += kThreads) {
+    const int wy_ = r / ww, wx_ = r - wy_ * ww;
+    s_goff[r] = (hd.y_lo + wy_) * W + hd.x_lo + wx_;
+  }
+  __syncthreads();
+  // ---- stage with cp.async: warp -> plane, lanes -> window pixels
+  for (int r = lane; r < area; r += 32) {
+    const int g = s_goff[r];
+    float* d = s_win + r;
+    const float* p = plane0 + g;
+#pragma unroll 4
+    for (int c = warp; c < nc; c += kWarps) cp_async4(d + c * area, p + (size_t)c * HW);
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  // ---- compute: lane = bin (descriptor in registers), loop over channels; coalesced stores
+  if (has_bin) {
+    const float* w = s_win + (size_t)grp * area;
+    float* op = o + (size_t)grp * bins + b;
+    const int cstep = groups * area, ostep = groups * bins;
+    if (okb) {
+#pragma unroll 4
+      for (int c = grp; c < nc; c += groups) {
+        *op = bilerp(w[o00], w[o01], w[o10], w[o11], wx, wy);
+        w += cstep; op += ostep;
+      }
+    } else {
+      for (int c = grp; c < nc; c += groups) { *op = extrap; op += ostep; }
     }
   }
 }
@@ -273,7 +256,7 @@ roi_align_fwd_nhwc_kernel(const float* __restrict__ feat, const float* __restric
                           int num_boxes, int batch, int H, int W, int PH, int PW, int C,
                           float extrap, float* __restrict__ out) {
   extern __shared__ __align__(16) float4 s_px[];   // [area][32] float4 = 128 channels per pixel
-  float* s_tile = (float*)(s_px + kNhwcStageArea * 32);   // CHW only: [128][bins]
+  float* s_tile = (float*)(s_px + (kNhwcUseStaging ? kNhwcStageArea * 32 : 0));   // CHW only: [128][bins]
   __shared__ AxisTab ty, tx;
   __shared__ RoiHead hd;
   __shared__ int s_goff[kNhwcStageArea];
@@ -504,14 +487,13 @@ int ROIAlignForwardLaucher(const float* image_ptr, const float* boxes_ptr, int n
   if (num_boxes <= 0 || depth <= 0) return MB200_OK;
   if (crop_height <= 0 || crop_width <= 0 || image_height <= 0 || image_width <= 0) return MB200_ERR_ARG;
   const int bins = crop_height * crop_width;
-  const int chunks = mb200_div_up(depth, kLanes * kPasses);
+  const int chunks = mb200_div_up(depth, kChunkN);
   if (crop_height <= kMaxCrop && crop_width <= kMaxCrop && bins <= kMaxBins && chunks <= 65535) {
     dim3 grid(num_boxes, chunks);
-    const size_t smem = ((size_t)kLanes * bins + (size_t)kStageMaxArea * kWinStride) * sizeof(float);
+    const size_t smem = (size_t)kChunkN * kStageMaxArea * sizeof(float);   // 49 KB
     static bool attr_set = false;
     if (!attr_set) {
-      MB200_CHECK(cudaFuncSetAttribute(roi_align_fwd_nchw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)(((size_t)kLanes * kMaxBins + (size_t)kStageMaxArea * kWinStride) * sizeof(float))));
+      MB200_CHECK(cudaFuncSetAttribute(roi_align_fwd_nchw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       attr_set = true;
     }
     roi_align_fwd_nchw_kernel<<<grid, kThreads, smem, stream>>>(
@@ -560,7 +542,7 @@ static int roi_align_nhwc_launch(bool chw, const float* image_nhwc, const float*
   const int bins = crop_height * crop_width;
   if (depth % 4 == 0 && ((((uintptr_t)image_nhwc) | ((uintptr_t)crops)) & 15) == 0) {
     dim3 grid(num_boxes, mb200_div_up(depth, kChunkNHWC));
-    const size_t win = (size_t)kNhwcStageArea * 32 * sizeof(float4);
+    const size_t win = kNhwcUseStaging ? (size_t)kNhwcStageArea * 32 * sizeof(float4) : 0;
     const size_t max_tile = (size_t)kChunkNHWC * kMaxBins * sizeof(float);
     static bool attr_set = false;
     if (!attr_set) {

@@ -1,0 +1,76 @@
+"""Flat-buffer SGD for the relation model's trainable parameters: same update rule as the caller's
+`clip_grad_norm(..., max_norm=conf.clip)` + `optim.SGD(params, lr, momentum=0.9, weight_decay=conf.l2)`
+(models/train_rels.py:57-70,145-150) — including the lr/10 group for the VGG fc layers — but every
+parameter and gradient lives in ONE contiguous buffer per group, so that
+  * the global gradient norm is one reduction,
+  * the data-parallel gradient all-reduce is one NCCL call on the flat gradient (no bucket copies),
+  * clip + weight decay + momentum + update + gradient zeroing is one fused kernel (csrc/optim.cu).
+Parameters stay ordinary nn.Parameters (names / state dict unchanged); their storage is re-pointed."""
+import torch
+import torch.distributed as dist
+
+import motifs_cabi as _c
+from lib import tc_ops
+
+
+class FlatGroup(object):
+    def __init__(self, params, lr):
+        self.params = params
+        self.lr = lr
+        dev = params[0].device
+        offs, n = [], 0
+        for p in params:
+            offs.append(n)
+            n += (p.numel() + 3) // 4 * 4            # keep every view 16-byte aligned
+        self.n = n
+        self.flat_p = torch.zeros(n, device=dev, dtype=torch.float32)
+        self.flat_g = torch.zeros(n, device=dev, dtype=torch.float32)
+        self.flat_m = torch.zeros(n, device=dev, dtype=torch.float32)
+        with torch.no_grad():
+            for p, o in zip(params, offs):
+                view = self.flat_p[o:o + p.numel()].view_as(p)
+                view.copy_(p.data)
+                p.data = view
+                p.grad = self.flat_g[o:o + p.numel()].view_as(p)
+
+
+class FlatSGD(object):
+    """groups: list of (params, lr). momentum / weight_decay / max_norm shared (train_rels.py:66,145)."""
+
+    def __init__(self, groups, momentum=0.9, weight_decay=1e-4, max_norm=5.0):
+        self.groups = [FlatGroup([p for p in ps if p.requires_grad], lr) for ps, lr in groups if len(ps)]
+        self.momentum, self.weight_decay, self.max_norm = momentum, weight_decay, max_norm
+        self.steps = 0
+        tc_ops.bump_weight_epoch()       # storages moved
+
+    def zero_grad(self, set_to_none=False):
+        """Gradients are zeroed by the fused step itself; kept for API symmetry (never set to None:
+        autograd accumulates into the flat views)."""
+        if self.steps == 0:
+            for g in self.groups:
+                g.flat_g.zero_()
+
+    def all_reduce_grads(self):
+        """Data-parallel average: ONE all-reduce per group on the flat gradient buffer."""
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+            return
+        works = [dist.all_reduce(g.flat_g, op=dist.ReduceOp.SUM, async_op=True) for g in self.groups]
+        inv = 1.0 / dist.get_world_size()
+        for w, g in zip(works, self.groups):
+            w.wait()
+            g.flat_g.mul_(inv)
+
+    def step(self):
+        norms = torch.stack([torch.linalg.vector_norm(g.flat_g) for g in self.groups])
+        total = torch.linalg.vector_norm(norms).reshape(1).contiguous()
+        lib = _c.load()
+        first = 1 if self.steps == 0 else 0
+        for g in self.groups:
+            with torch.cuda.device(g.flat_p.device):
+                rc = lib.mb200_sgd_momentum_clip(_c.ptr(g.flat_p), _c.ptr(g.flat_g), _c.ptr(g.flat_m), g.n, float(g.lr),
+                                                 float(self.momentum), float(self.weight_decay), _c.ptr(total),
+                                                 float(self.max_norm), first, 1, _c.cur_stream())
+            _c.check(rc, "mb200_sgd_momentum_clip")
+        self.steps += 1
+        tc_ops.bump_weight_epoch()       # raw-pointer update: invalidate the bf16 split caches
+        return total

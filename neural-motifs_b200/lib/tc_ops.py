@@ -108,13 +108,20 @@ def gemm(A, B, bias=None, relu=False, want_f32=True, want_split=False):
 
 # ------------------------------------------------------------------ weight split cache
 _cache = {}
+WEIGHT_EPOCH = 0     # bumped by optimizers that update parameters through raw pointers (lib/fused_optim.py)
+
+
+def bump_weight_epoch():
+    global WEIGHT_EPOCH
+    WEIGHT_EPOCH += 1
+
 
 
 def _cached(param, kind, maker):
     """Split copies of a parameter are rebuilt only when the parameter changes (optimizer steps
     bump `_version`); frozen weights are split once."""
     key = (id(param), kind)
-    ver = (param.data_ptr(), param._version, tuple(param.shape))
+    ver = (param.data_ptr(), param._version, tuple(param.shape), WEIGHT_EPOCH if param.requires_grad else 0)
     hit = _cache.get(key)
     if hit is not None and hit[0] == ver:
         return hit[1]
@@ -126,7 +133,7 @@ def _cached(param, kind, maker):
 def _cached_view(base, tag, view, maker):
     """Like _cached, for a view (slice) of the flat parameter `base`; `tag` names the slice."""
     key = (id(base), tag)
-    ver = (base.data_ptr(), base._version, tuple(view.shape))
+    ver = (base.data_ptr(), base._version, tuple(view.shape), WEIGHT_EPOCH if base.requires_grad else 0)
     hit = _cache.get(key)
     if hit is not None and hit[0] == ver:
         return hit[1]

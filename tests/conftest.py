@@ -10,6 +10,10 @@ for p in (ROOT, PKG):
         sys.path.insert(0, p)
 
 
+import faulthandler
+faulthandler.dump_traceback_later(900, exit=True)    # never let a wedged kernel burn the GPU lease
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 

@@ -98,3 +98,26 @@ def test_maxpool_and_vgg_features_vs_torch(cuda):
     assert tuple(out.shape) == (2, 6, 10, 512)
     # 13 stacked layers: north-star bar is 1e-3; the bf16x3 path should sit near 1e-4
     assert relerr(out.permute(0, 3, 1, 2), ref) < 3e-4, relerr(out.permute(0, 3, 1, 2), ref)
+
+
+def test_flat_sgd_matches_torch_sgd_with_clip(cuda):
+    """lib/fused_optim.FlatSGD == clip_grad_norm_ + torch.optim.SGD(momentum, weight_decay), 3 steps."""
+    from lib.fused_optim import FlatSGD
+    torch.manual_seed(0)
+    shapes = [(33, 7), (5,), (1000, 129), (3, 3, 3)]
+    a = [torch.nn.Parameter(torch.randn(s, device=cuda)) for s in shapes]
+    b = [torch.nn.Parameter(p.detach().clone()) for p in a]
+    ref = torch.optim.SGD([{'params': b[:2], 'lr': 0.01}, {'params': b[2:]}], lr=0.1, momentum=0.9, weight_decay=1e-4)
+    opt = FlatSGD([(a[:2], 0.01), (a[2:], 0.1)], momentum=0.9, weight_decay=1e-4, max_norm=5.0)
+    opt.zero_grad()
+    for step in range(3):
+        grads = [torch.randn(s, device=cuda) * (3.0 if step == 1 else 0.01) for s in shapes]   # step 1 clips
+        for p, q, g in zip(a, b, grads):
+            p.grad.add_(g)          # autograd accumulates into the flat views
+            q.grad = g.clone()
+        torch.nn.utils.clip_grad_norm_(b, 5.0)
+        ref.step()
+        opt.step()
+        for p, q in zip(a, b):
+            assert torch.allclose(p, q, rtol=1e-5, atol=1e-6), float((p - q).abs().max())
+            assert float(p.grad.abs().max()) == 0.0

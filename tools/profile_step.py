@@ -7,14 +7,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "neural-motifs_b200"))
 import torch
 import bench
-from lib.data_parallel import GradAllReducer
 from dataloaders.synthetic import make_numpy_batch, SyntheticBlob
 
 ap = argparse.ArgumentParser(); ap.add_argument("--steps", type=int, default=2); a = ap.parse_args()
 dev = torch.device("cuda:0")
 model = bench.build_model(dev)
 opt = bench.get_optim(model, 6e-3)
-red = GradAllReducer(model.parameters())
+red = None
 blob = SyntheticBlob(make_numpy_batch(6, seed=0), dev); blob.scatter()
 for i in range(a.steps):
     torch.cuda.nvtx.range_push("step%d" % i)
