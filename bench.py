@@ -249,9 +249,51 @@ def run_b200(args):
         "clocks": clocks,
         "final_loss": losses[-1] if losses else None,
     }
+    if world == 1:
+        out["roi_align"] = roi_align_microbench(dev, pk, kind)
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(sample_images=2)
     print(json.dumps(out), flush=True)
+
+
+def roi_align_microbench(dev, pk, kind):
+    """BASELINE.json metric (ii): RoIAlign achieved GB/s vs the measured HBM peak, config 4
+    (1024 boxes x 7x7 x 512 ch on a 37x37 map). Algorithmic bytes: output write +
+    each feature element once + rois = 105.6 MB. L2 flushed between iterations (256 MB memset)."""
+    import numpy as np
+    import torch
+    import motifs_cabi as C
+    from lib.fpn.roi_align.functions.roi_align import normalize_rois
+    rng = np.random.RandomState(0)
+    N, Cn, B = 1024, 512, 1
+    x1 = rng.uniform(0, 400, N); y1 = rng.uniform(0, 400, N)
+    w = rng.uniform(32, 190, N); h = rng.uniform(32, 190, N)
+    rois = np.concatenate([np.zeros((N, 1)), np.stack([x1, y1, np.minimum(x1 + w, 591), np.minimum(y1 + h, 591)], 1)], 1)
+    rn = normalize_rois(torch.from_numpy(rois.astype(np.float32)).to(dev), 37, 37, 1 / 16)
+    feat = torch.randn(B, Cn, 37, 37, device=dev)
+    feat_nhwc = feat.permute(0, 2, 3, 1).contiguous()
+    out = torch.empty(N, Cn, 7, 7, device=dev)
+    flush = torch.empty(64 * 1024 * 1024, device=dev)
+    lib = C.load()
+    alg = N * Cn * 49 * 4 + B * Cn * 37 * 37 * 4 + N * 20
+
+    def run(fn):
+        ts = []
+        for i in range(13):
+            flush.zero_()
+            a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record(); torch.cuda.synchronize()
+            if i >= 3:
+                ts.append(a.elapsed_time(b) * 1e3)
+        return float(np.median(ts))
+    st = C.cur_stream()
+    t_nchw = run(lambda: lib.ROIAlignForwardLaucher(C.ptr(feat), C.ptr(rn), N, B, 37, 37, 7, 7, Cn, 0.0, C.ptr(out), st))
+    t_nhwc = run(lambda: lib.mb200_roi_align_forward_nhwc(C.ptr(feat_nhwc), C.ptr(rn), N, B, 37, 37, 7, 7, Cn, 0.0, C.ptr(out), st))
+    peak = float(pk["hbm_gbs"])
+    return {"config": "N=1024 boxes, 7x7, C=512, B=1 (BASELINE configs[3])", "algorithmic_bytes": alg, "bound": "hbm",
+            "peak": peak, "peak_kind": "%s copy bandwidth" % kind, "unit": "GB/s",
+            "drop_in_nchw": {"us": t_nchw, "achieved": alg / t_nchw / 1e3, "frac": alg / t_nchw / 1e3 / peak},
+            "pipeline_nhwc": {"us": t_nhwc, "achieved": alg / t_nhwc / 1e3, "frac": alg / t_nhwc / 1e3 / peak}}
 
 
 # ------------------------------------------------------------------------------------------ CPU arm (oracle port)

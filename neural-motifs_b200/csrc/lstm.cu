@@ -36,6 +36,24 @@ constexpr int kBTb = 8;       // batch rows per tile, backward (dG rows of 5H fl
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 
+// Grid-wide barrier for the cooperative (co-resident) launch: monotonically increasing arrival
+// counter in global memory, release by fence + atomic, acquire by ld.acquire spinning. Cheaper than
+// cooperative_groups' grid.sync() for 128 CTAs, and it is the only thing on the per-step critical path.
+__device__ unsigned int g_lstm_barrier[2];
+
+__device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(bar, 1u);
+    unsigned int v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+    } while (v < target);
+  }
+  __syncthreads();
+}
+
 struct FwdArgs {
   int H, B, T, dir, training;
   const float* P;        // [T,B,6H] input projection (aliases gates when training)
@@ -46,6 +64,7 @@ struct FwdArgs {
   float* c;              // [T+1,B,H]
   float* gates;          // [T,B,6H] or nullptr
   const int* lengths;    // DEV [B], descending
+  unsigned int* barrier; // zeroed before launch
 };
 
 __device__ __forceinline__ int pick_ks(int rows) {
@@ -56,7 +75,6 @@ __device__ __forceinline__ int pick_ks(int rows) {
 }
 
 __global__ void __launch_bounds__(kThreads, 1) lstm_fwd_kernel(FwdArgs a) {
-  cg::grid_group grid = cg::this_grid();
   extern __shared__ float smem[];
   const int H = a.H, B = a.B, T = a.T;
   const int ldh = H + 4;
@@ -158,7 +176,7 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_fwd_kernel(FwdArgs a) {
       }
       __syncthreads();
     }
-    grid.sync();
+    grid_barrier(a.barrier, (unsigned int)(step + 1) * gridDim.x);
   }
 }
 
@@ -174,10 +192,10 @@ struct BwdArgs {
   float* c_grad;          // [T+1,B,H] (zero-initialised)
   float* dG;              // [T,B,6H]  (zero-initialised) gate gradients of every step
   const int* lengths;
+  unsigned int* barrier;  // zeroed before launch
 };
 
 __global__ void __launch_bounds__(kThreads, 1) lstm_bwd_kernel(BwdArgs a) {
-  cg::grid_group grid = cg::this_grid();
   extern __shared__ float smem[];
   const int H = a.H, B = a.B, T = a.T;
   const int H5 = 5 * H;
@@ -230,16 +248,22 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_bwd_kernel(BwdArgs a) {
       D[(size_t)5 * H] = d_h * (1 - r_gate);
       a.c_grad[(size_t)(t + 1) * BH + e] = forget_gate * d_c;
     }
-    grid.sync();
+    grid_barrier(a.barrier, (unsigned int)(step + 1) * gridDim.x);
     // (B) h_grad[t+1][b][k] = sum_{5H} dG[t][b][:5H] * W_h[k][:]  for k in this CTA's units
     float* hg = a.h_grad + (size_t)(t + 1) * BH;
     for (int b0 = 0; b0 < cov; b0 += kBTb) {
       const int rows = min(kBTb, cov - b0);
       const int vec_per_row = H5 / 4;
-      for (int idx = tid; idx < rows * vec_per_row; idx += kThreads) {
-        const int r = idx / vec_per_row, v = idx - r * vec_per_row;
-        const float4 x = __ldcg((const float4*)(a.dG + ((size_t)t * B + b0 + r) * 6 * H) + v);
-        *(float4*)(gs + (size_t)r * ldg + 4 * v) = x;
+      // all loads of a row batch are issued before the first shared-memory store (L2 latency ~1 us
+      // per dependent round trip is the cost that matters here)
+      for (int v0 = tid; v0 < vec_per_row; v0 += kThreads) {
+        float4 x[kBTb];
+#pragma unroll
+        for (int r = 0; r < kBTb; ++r)
+          if (r < rows) x[r] = __ldcg((const float4*)(a.dG + ((size_t)t * B + b0 + r) * 6 * H) + v0);
+#pragma unroll
+        for (int r = 0; r < kBTb; ++r)
+          if (r < rows) *(float4*)(gs + (size_t)r * ldg + 4 * v0) = x[r];
       }
       __syncthreads();
       const int KS = pick_ks(rows);
@@ -274,6 +298,17 @@ __global__ void colsum_accum_kernel(const float* __restrict__ in, int rows, int 
 
 size_t fwd_smem_bytes(int H, int B) { return ((size_t)H * 5 * kUJ + (size_t)kBTf * (H + 4) + B) * 4; }
 size_t bwd_smem_bytes(int H, int B) { return ((size_t)kUJ * 5 * H + (size_t)kBTb * (5 * H + 4) + B) * 4; }
+
+unsigned int* barrier_ptr(int which, cudaStream_t stream) {
+  static unsigned int* base = nullptr;
+  if (!base) {
+    void* p = nullptr;
+    if (cudaGetSymbolAddress(&p, g_lstm_barrier) != cudaSuccess) return nullptr;
+    base = (unsigned int*)p;
+  }
+  cudaMemsetAsync(base + which, 0, sizeof(unsigned int), stream);
+  return base + which;
+}
 
 int check_coop(const void* fn, int grid, size_t smem) {
   int dev = 0, coop = 0, sms = 0, per_sm = 0;
@@ -329,6 +364,8 @@ int mb200_highway_lstm_forward(int inputSize, int hiddenSize, int miniBatch, int
     a.P = P; a.Wh = Wh; a.bias = bias + (size_t)layer * 5 * H; a.dropout = dropout + (size_t)layer * B * H;
     a.h = h_data + (size_t)layer * acc; a.c = c_data + (size_t)layer * acc;
     a.gates = gates ? P : nullptr; a.lengths = lengths_dev;
+    a.barrier = barrier_ptr(0, stream);
+    if (!a.barrier) return MB200_ERR_CUDA;
     void* args[] = {&a};
     MB200_CHECK(cudaLaunchCooperativeKernel((const void*)lstm_fwd_kernel, dim3(grid), dim3(kThreads), args, smem, stream));
   }
@@ -368,6 +405,8 @@ int mb200_highway_lstm_backward(int inputSize, int hiddenSize, int miniBatch, in
     a.gates = gates_out + (size_t)layer * TB * 6 * H; a.dropout = dropout_in + (size_t)layer * BH;
     a.h_grad = h_data_grad + (size_t)layer * acc; a.c_grad = c_data_grad + (size_t)layer * acc;
     a.dG = dG_scratch; a.lengths = lengths_dev;
+    a.barrier = barrier_ptr(1, stream);
+    if (!a.barrier) return MB200_ERR_CUDA;
     void* args[] = {&a};
     MB200_CHECK(cudaLaunchCooperativeKernel((const void*)lstm_bwd_kernel, dim3(grid), dim3(kThreads), args, smem, stream));
     // dX = dG * W_i^T   (:278-289), all steps at once
@@ -412,6 +451,8 @@ int mb200_highway_lstm_layer_forward(int hiddenSize, int miniBatch, int seqLengt
   FwdArgs a;
   a.H = H; a.B = B; a.T = TT; a.dir = dir; a.training = gates != nullptr;
   a.P = P; a.Wh = Wh; a.bias = bias; a.dropout = dropout; a.h = h; a.c = c; a.gates = gates; a.lengths = lengths_dev;
+  a.barrier = barrier_ptr(0, stream);
+  if (!a.barrier) return MB200_ERR_CUDA;
   void* args[] = {&a};
   MB200_CHECK(cudaLaunchCooperativeKernel((const void*)lstm_fwd_kernel, dim3(grid), dim3(kThreads), args, smem, stream));
   return MB200_OK;
@@ -434,6 +475,8 @@ int mb200_highway_lstm_layer_backward(int hiddenSize, int miniBatch, int seqLeng
   BwdArgs a;
   a.H = H; a.B = B; a.T = TT; a.dir = dir; a.out_grad = out_grad; a.Wh = Wh; a.h = h; a.c = c; a.gates = gates;
   a.dropout = dropout; a.h_grad = h_grad; a.c_grad = c_grad; a.dG = dG; a.lengths = lengths_dev;
+  a.barrier = barrier_ptr(1, stream);
+  if (!a.barrier) return MB200_ERR_CUDA;
   void* args[] = {&a};
   MB200_CHECK(cudaLaunchCooperativeKernel((const void*)lstm_bwd_kernel, dim3(grid), dim3(kThreads), args, smem, stream));
   return MB200_OK;

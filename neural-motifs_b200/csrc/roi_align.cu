@@ -250,28 +250,56 @@ constexpr int kNhwcStageArea = 96;       // windows up to 96 px are staged: 96 *
 constexpr bool kNhwcUseStaging = false;  // measured on B200: L1 already serves the re-reads (39 us vs 49 us staged)
 // CHW == false: out [N, bins, C] (bin-major).  CHW == true: out [N, C, bins] — the reference's
 // [N,C,PH,PW] layout — produced through a shared [128][bins] tile and contiguous vector stores.
+// ncu on the first version: issue-bound (34 thread-instructions per output, 0.74 issue slots/cycle):
+// per-bin index math is now done ONCE per CTA into a shared descriptor table (two 16-byte broadcast
+// reads per bin), offsets are 32-bit element offsets, and the bin loop is unrolled by two so eight
+// 16-byte loads are in flight per lane.
+struct __align__(16) NhwcBin { int o00, o01, o10, o11; };           // element offsets of the 4 corners
+struct __align__(16) NhwcBinW { float wx, wy; int ok; int pad; };
+
 template <bool CHW>
 __global__ void __launch_bounds__(kThreads)
 roi_align_fwd_nhwc_kernel(const float* __restrict__ feat, const float* __restrict__ boxes,
                           int num_boxes, int batch, int H, int W, int PH, int PW, int C,
                           float extrap, float* __restrict__ out) {
-  extern __shared__ __align__(16) float4 s_px[];   // [area][32] float4 = 128 channels per pixel
-  float* s_tile = (float*)(s_px + (kNhwcUseStaging ? kNhwcStageArea * 32 : 0));   // CHW only: [128][bins]
+  extern __shared__ __align__(16) float s_tile[];          // CHW only: [128][bins]
   __shared__ AxisTab ty, tx;
   __shared__ RoiHead hd;
-  __shared__ int s_goff[kNhwcStageArea];
+  __shared__ NhwcBin s_bin[kMaxBins];
+  __shared__ NhwcBinW s_binw[kMaxBins];
   const int n = blockIdx.x;
   const int c0 = blockIdx.y * kChunkNHWC;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int kWarps = kThreads / 32;
   const int bins = PH * PW;
   roi_preamble(boxes, n, batch, H, W, PH, PW, ty, tx, hd);
+  for (int b = tid; b < bins; b += kThreads) {
+    const int y = b / PW, x = b - y * PW;
+    NhwcBin d; NhwcBinW w;
+    w.ok = hd.bad_batch ? 2 : ((ty.ok[y] & tx.ok[x]) ? 1 : 0);
+    w.wx = tx.lerp[x]; w.wy = ty.lerp[y]; w.pad = 0;
+    d.o00 = (ty.lo[y] * W + tx.lo[x]) * C; d.o01 = (ty.lo[y] * W + tx.hi[x]) * C;
+    d.o10 = (ty.hi[y] * W + tx.lo[x]) * C; d.o11 = (ty.hi[y] * W + tx.hi[x]) * C;
+    if (w.ok != 1) { d.o00 = d.o01 = d.o10 = d.o11 = 0; }
+    s_bin[b] = d; s_binw[b] = w;
+  }
+  __syncthreads();
   const int c = c0 + 4 * lane;
   const bool lane_ok = c < C;
+  const float* img = feat + (size_t)(hd.bad_batch ? 0 : hd.b_in) * H * W * C + (lane_ok ? c : 0);
   float* o = out + (size_t)n * bins * C + c;
-  const float* img = feat + (size_t)(hd.bad_batch ? 0 : hd.b_in) * H * W * C + c;
-  const int area = hd.wh * hd.ww;
-  const bool staged = kNhwcUseStaging && hd.any_ok && area <= kNhwcStageArea;
+
+  auto sample = [&](int b) -> float4 {
+    const NhwcBin d = s_bin[b];
+    const NhwcBinW w = s_binw[b];
+    const float4 tl = __ldg((const float4*)(img + d.o00)), tr = __ldg((const float4*)(img + d.o01));
+    const float4 bl = __ldg((const float4*)(img + d.o10)), br = __ldg((const float4*)(img + d.o11));
+    float4 v;
+    v.x = bilerp(tl.x, tr.x, bl.x, br.x, w.wx, w.wy); v.y = bilerp(tl.y, tr.y, bl.y, br.y, w.wx, w.wy);
+    v.z = bilerp(tl.z, tr.z, bl.z, br.z, w.wx, w.wy); v.w = bilerp(tl.w, tr.w, bl.w, br.w, w.wx, w.wy);
+    if (w.ok != 1) { const float e = (w.ok == 2) ? 0.f : extrap; v = make_float4(e, e, e, e); }
+    return v;
+  };
   auto emit = [&](int b, const float4& v) {
     if (CHW) {
       float* t = s_tile + (size_t)(4 * lane) * bins + b;
@@ -280,8 +308,14 @@ roi_align_fwd_nhwc_kernel(const float* __restrict__ feat, const float* __restric
       *(float4*)(o + (size_t)b * C) = v;
     }
   };
-  auto flush = [&]() {   // CHW: the chunk's [nc][bins] block is one contiguous run in global memory
-    if (!CHW) return;
+  int b = warp;
+  for (; b + kWarps < bins; b += 2 * kWarps) {        // two bins per iteration: 8 loads in flight
+    const float4 v0 = sample(b);
+    const float4 v1 = sample(b + kWarps);
+    emit(b, v0); emit(b + kWarps, v1);
+  }
+  if (b < bins) emit(b, sample(b));
+  if (CHW) {   // the chunk's [nc][bins] block is one contiguous run in global memory
     __syncthreads();
     const int nc = min(kChunkNHWC, C - c0);
     float* dst = out + ((size_t)n * C + c0) * bins;
@@ -291,66 +325,7 @@ roi_align_fwd_nhwc_kernel(const float* __restrict__ feat, const float* __restric
     } else {
       for (int i = tid; i < total; i += kThreads) dst[i] = s_tile[i];
     }
-  };
-  if (staged) {
-    const int ww = hd.ww;
-    for (int r = tid; r < area; r += kThreads) {
-      const int wy_ = r / ww, wx_ = r - wy_ * ww;
-      s_goff[r] = (hd.y_lo + wy_) * W + hd.x_lo + wx_;
-    }
-    __syncthreads();
-    // each pixel of the window is fetched from L2 exactly once (4 loads in flight per lane)
-    for (int rb = warp; rb < area; rb += 4 * kWarps) {
-      float4 v[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int r = rb + j * kWarps;
-        v[j] = (r < area && lane_ok) ? __ldg((const float4*)(img + (size_t)s_goff[r] * C)) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int r = rb + j * kWarps;
-        if (r < area) s_px[r * 32 + lane] = v[j];
-      }
-    }
-    __syncthreads();
-    for (int b = warp; b < bins; b += kWarps) {
-      const int y = b / PW, x = b - y * PW;
-      float4 v;
-      if (!(ty.ok[y] & tx.ok[x])) v = make_float4(extrap, extrap, extrap, extrap);
-      else {
-        const int yt = (ty.lo[y] - hd.y_lo) * ww, yb = (ty.hi[y] - hd.y_lo) * ww;
-        const int xl = tx.lo[x] - hd.x_lo, xr = tx.hi[x] - hd.x_lo;
-        const float4 tl = s_px[(yt + xl) * 32 + lane], tr = s_px[(yt + xr) * 32 + lane];
-        const float4 bl = s_px[(yb + xl) * 32 + lane], br = s_px[(yb + xr) * 32 + lane];
-        const float wx = tx.lerp[x], wy = ty.lerp[y];
-        v.x = bilerp(tl.x, tr.x, bl.x, br.x, wx, wy); v.y = bilerp(tl.y, tr.y, bl.y, br.y, wx, wy);
-        v.z = bilerp(tl.z, tr.z, bl.z, br.z, wx, wy); v.w = bilerp(tl.w, tr.w, bl.w, br.w, wx, wy);
-      }
-      emit(b, v);
-    }
-    flush();
-    return;
   }
-  for (int b = warp; b < bins; b += kWarps) {
-    const int y = b / PW, x = b - y * PW;
-    float4 v;
-    if (hd.bad_batch) v = make_float4(0.f, 0.f, 0.f, 0.f);
-    else if (!(ty.ok[y] & tx.ok[x])) v = make_float4(extrap, extrap, extrap, extrap);
-    else if (!lane_ok) v = make_float4(0.f, 0.f, 0.f, 0.f);
-    else {
-      const float* r0 = img + (size_t)(ty.lo[y] * W) * C;
-      const float* r1 = img + (size_t)(ty.hi[y] * W) * C;
-      const size_t xl = (size_t)tx.lo[x] * C, xr = (size_t)tx.hi[x] * C;
-      const float4 tl = __ldg((const float4*)(r0 + xl)), tr = __ldg((const float4*)(r0 + xr));
-      const float4 bl = __ldg((const float4*)(r1 + xl)), br = __ldg((const float4*)(r1 + xr));
-      const float wx = tx.lerp[x], wy = ty.lerp[y];
-      v.x = bilerp(tl.x, tr.x, bl.x, br.x, wx, wy); v.y = bilerp(tl.y, tr.y, bl.y, br.y, wx, wy);
-      v.z = bilerp(tl.z, tr.z, bl.z, br.z, wx, wy); v.w = bilerp(tl.w, tr.w, bl.w, br.w, wx, wy);
-    }
-    emit(b, v);
-  }
-  flush();
 }
 
 // scalar NHWC fallback for channel counts that are not a multiple of 4
@@ -542,7 +517,7 @@ static int roi_align_nhwc_launch(bool chw, const float* image_nhwc, const float*
   const int bins = crop_height * crop_width;
   if (depth % 4 == 0 && ((((uintptr_t)image_nhwc) | ((uintptr_t)crops)) & 15) == 0) {
     dim3 grid(num_boxes, mb200_div_up(depth, kChunkNHWC));
-    const size_t win = kNhwcUseStaging ? (size_t)kNhwcStageArea * 32 * sizeof(float4) : 0;
+    const size_t win = 0;
     const size_t max_tile = (size_t)kChunkNHWC * kMaxBins * sizeof(float);
     static bool attr_set = false;
     if (!attr_set) {

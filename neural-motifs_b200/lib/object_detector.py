@@ -22,6 +22,7 @@ from lib.fpn.box_utils import bbox_preds_fused, center_size, bbox_overlaps
 from lib.fpn.generate_anchors import generate_anchors
 from lib.fpn.nms.functions.nms import apply_nms, nms_segments
 from lib.fpn.proposal_assignments.proposal_assignments_gtbox import proposal_assignments_gtbox
+from lib.fpn.proposal_assignments.proposal_assignments_det import proposal_assignments_det
 from lib.fpn.roi_align.functions.roi_align import RoIAlignFunction, roi_align_from_nhwc
 from lib.pytorch_misc import image_segments, gather_nd
 
@@ -163,7 +164,9 @@ class ObjectDetector(nn.Module):
                                  "at the same time isn't supported")
             if self.mode == 'refinerels':
                 return rois, None, None, rpn_scores, rpn_box_deltas, None
-            raise NotImplementedError("proposal_assignments_det (detector training) is not built yet (SURVEY.md §8f f1)")
+            all_rois, labels, bbox_targets = proposal_assignments_det(
+                rois, gt_boxes.detach(), gt_classes.detach(), image_offset, fg_thresh=0.5, rng=getattr(self, "rng", np.random))
+            return all_rois, labels, bbox_targets, rpn_scores, rpn_box_deltas, None
         return rois, None, None, None, None, None
 
     def gt_boxes(self, fmap, im_sizes, image_offset, gt_boxes=None, gt_classes=None, gt_rels=None,
@@ -188,7 +191,10 @@ class ObjectDetector(nn.Module):
                                     pre_nms_topn=12000 if self.training and self.mode == 'rpntrain' else 6000,
                                     post_nms_topn=2000 if self.training and self.mode == 'rpntrain' else 1000)
         if self.training:
-            raise NotImplementedError("proposal_assignments_det (detector training) is not built yet (SURVEY.md §8f f1)")
+            all_rois, labels, bbox_targets = proposal_assignments_det(
+                rois, gt_boxes.detach(), gt_classes.detach(), image_offset, fg_thresh=0.5, rng=getattr(self, "rng", np.random))
+            all_rois = torch.cat((all_rois, rois), 0)       # object_detector.py:254-255
+            return all_rois, labels, bbox_targets, None, None, None
         return rois, None, None, None, None, None
 
     def get_boxes(self, *args, **kwargs):

@@ -328,7 +328,8 @@ class RelModel(nn.Module):
             from lib.fpn.proposal_assignments.rel_assignments import rel_assignments
             result.rel_labels = rel_assignments(im_inds.detach(), boxes.detach(), result.rm_obj_labels.detach(),
                                                 gt_boxes.detach(), gt_classes.detach(), gt_rels.detach(), image_offset,
-                                                filter_non_overlap=True, num_sample_per_gt=1)
+                                                filter_non_overlap=True, num_sample_per_gt=1,
+                                                rng=getattr(self.detector, "rng", np.random))
         rel_inds = self.get_rel_inds(result.rel_labels, im_inds, boxes)
         rois = torch.cat((im_inds[:, None].float(), boxes), 1)
         result.obj_fmap = self.obj_feature_map(result.fmap.detach(), rois)

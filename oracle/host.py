@@ -116,3 +116,107 @@ def transpose_packed_sequence_inds(lengths):
         cum[:ptr + 1] += 1
         new_lens.append(ptr + 1)
     return np.concatenate(new_inds, 0), new_lens
+
+
+def rel_assignments(im_inds, rois, roi_gtlabels, gt_boxes, gt_classes, gt_rels, image_offset, rng, fg_thresh=0.5,
+                    num_sample_per_gt=4, filter_non_overlap=True):
+    """lib/fpn/proposal_assignments/rel_assignments.py:15-145 on numpy arrays, nested loops as written
+    there; `rng` replaces numpy.random (same call order). Returns int64 [n,4]."""
+    fg_rels_per_image = int(np.round(REL_FG_FRACTION * 64))
+    gt_classes = np.array(gt_classes, copy=True); gt_rels = np.array(gt_rels, copy=True)
+    gt_classes[:, 0] -= image_offset
+    gt_rels[:, 0] -= image_offset
+    num_im = gt_classes[:, 0].max() + 1
+    rel_labels, num_box_seen = [], 0
+    for im_ind in range(num_im):
+        pred_ind = np.where(im_inds == im_ind)[0]
+        gt_ind = np.where(gt_classes[:, 0] == im_ind)[0]
+        gt_boxes_i = gt_boxes[gt_ind]
+        gt_classes_i = gt_classes[gt_ind, 1]
+        gt_rels_i = gt_rels[gt_rels[:, 0] == im_ind, 1:]
+        pred_boxes_i = rois[pred_ind]
+        labels_i = roi_gtlabels[pred_ind]
+        ious = ops.bbox_overlaps_f64(pred_boxes_i, gt_boxes_i)
+        is_match = (labels_i[:, None] == gt_classes_i[None]) & (ious >= fg_thresh)
+        pbi = ops.bbox_overlaps_f64(pred_boxes_i, pred_boxes_i)
+        if filter_non_overlap:
+            poss = (pbi < 1) & (pbi > 0)
+        else:
+            poss = (np.ones((len(pred_ind), len(pred_ind)), dtype=np.int64) - np.eye(len(pred_ind), dtype=np.int64)) > 0
+        poss = poss.copy()
+        poss[labels_i == 0] = 0
+        poss[:, labels_i == 0] = 0
+        fg_rels = []
+        for (from_gt, to_gt, rel_id) in gt_rels_i:
+            cand, score = [], []
+            for a in np.where(is_match[:, from_gt])[0]:
+                for b in np.where(is_match[:, to_gt])[0]:
+                    if a != b:
+                        cand.append((a, b, rel_id))
+                        score.append(ious[a, from_gt] * ious[b, to_gt])
+                        poss[a, b] = 0
+            if not cand:
+                continue
+            p = np.array(score); p = p / p.sum()
+            for k in rng.choice(p.shape[0], p=p, size=min(p.shape[0], num_sample_per_gt), replace=False):
+                fg_rels.append(cand[k])
+        fg_rels = np.array(fg_rels, dtype=np.int64)
+        if fg_rels.size > 0 and fg_rels.shape[0] > fg_rels_per_image:
+            fg_rels = fg_rels[rng.choice(fg_rels.shape[0], size=fg_rels_per_image, replace=False)]
+        elif fg_rels.size == 0:
+            fg_rels = np.zeros((0, 3), dtype=np.int64)
+        bg = np.column_stack(np.where(poss))
+        bg = np.column_stack((bg, np.zeros(bg.shape[0], dtype=np.int64)))
+        num_bg = min(64 - fg_rels.shape[0], bg.shape[0])
+        if bg.size > 0:
+            bg = bg[rng.choice(bg.shape[0], size=num_bg, replace=False)]
+        else:
+            bg = np.zeros((0, 3), dtype=np.int64)
+        if fg_rels.size == 0 and bg.size == 0:
+            bg = np.array([[0, 0, 0]], dtype=np.int64)
+        allr = np.concatenate((fg_rels, bg), 0)
+        allr[:, 0:2] += num_box_seen
+        allr = allr[np.lexsort((allr[:, 1], allr[:, 0]))]
+        rel_labels.append(np.column_stack((im_ind * np.ones(allr.shape[0], dtype=np.int64), allr)))
+        num_box_seen += pred_boxes_i.shape[0]
+    return np.concatenate(rel_labels, 0)
+
+
+def proposal_assignments_det(rois, gt_boxes, gt_classes, image_offset, rng, fg_thresh=0.5):
+    """lib/fpn/proposal_assignments/proposal_assignments_det.py:12-117 on numpy arrays (fp32 IoU as the
+    torch branch of box_utils.bbox_overlaps). Returns (rois [n,5] f32, labels [n] i64, targets [n,4] f32)."""
+    fg_per = int(np.round(256 * 0.25))
+    gt_img = gt_classes[:, 0] - image_offset
+    all_boxes = np.concatenate([rois[:, 1:], gt_boxes], 0).astype(np.float32)
+    ims = np.concatenate([rois[:, 0].astype(np.int64), gt_img], 0)
+    idx = np.argsort(ims, kind="stable")
+    im_sorted, all_boxes = ims[idx], all_boxes[idx]
+    out_r, out_l, out_t = [], [], []
+    for im in range(int(im_sorted[-1]) + 1):
+        g = np.where(gt_img == im)[0]
+        if g.size == 0:
+            continue
+        gs, ge = g[0], g[-1] + 1
+        t = np.where(im_sorted == im)[0]
+        ts, te = t[0], t[-1] + 1
+        ious = ops.bbox_overlaps_f32(all_boxes[ts:te], gt_boxes[gs:ge])
+        mo = ious.max(1)
+        ga = ious.argmax(1) + gs
+        fg = np.where(mo >= fg_thresh)[0]
+        nfg = min(fg_per, fg.shape[0])
+        if fg.size > 0:
+            fg = rng.choice(fg, size=nfg, replace=False)
+        bgi = np.where((mo < 0.5) & (mo >= 0.0))[0]
+        nbg = min(256 - nfg, bgi.size)
+        if bgi.size > 0:
+            bgi = rng.choice(bgi, size=nbg, replace=False)
+        keep = np.append(fg, bgi).astype(np.int64)
+        if keep.size == 0:
+            continue
+        lab = gt_classes[:, 1][ga[keep]].copy()
+        if nfg < lab.shape[0]:
+            lab[nfg:] = 0
+        out_r.append(np.column_stack((im_sorted[ts:te][keep].astype(np.float32), all_boxes[ts:te][keep])))
+        out_l.append(lab)
+        out_t.append(gt_boxes[ga[keep]])
+    return np.concatenate(out_r, 0), np.concatenate(out_l, 0), np.concatenate(out_t, 0)

@@ -105,3 +105,34 @@ def test_sgdet_eval_runs_and_is_consistent(cuda):
     assert (rels[:, 0] != rels[:, 1]).all()
     sc = pred[:, 1:].max(1) * scores[rels[:, 0]] * scores[rels[:, 1]]
     assert (np.diff(sc) <= 1e-7).all()
+
+
+def test_sgdet_train_step_runs(cuda):
+    """SGDet TRAINING forward+backward (scripts/refine_for_detection.sh): RPN -> NMS -> per-class NMS ->
+    IoU relabelling -> rel_assignments -> step-loop decoder (background labels) -> losses. No oracle for
+    this path (stochastic detections); checks shapes, label ranges, finite losses and gradients."""
+    from lib.fpn.anchor_targets import anchor_target_layer
+    prod, _ = build_pair('sgdet', seed=4)
+    prod = prod.to(cuda).train()
+    prod.detector.thresh = 0.0
+    prod.detector.rng = np.random.RandomState(0)
+    B = 2
+    nb = make_numpy_batch(B, seed=8, boxes_per_img=10, rels_per_img=8)
+    tai = []
+    for i in range(B):
+        gb = nb["gt_boxes"][nb["gt_classes"][:, 0] == i]
+        _, inds, _, _ = anchor_target_layer(gb, (592, 592), rng=np.random.RandomState(i))
+        tai.append(np.column_stack((np.full(inds.shape[0], i), inds)))
+    tai = torch.from_numpy(np.concatenate(tai).astype(np.int64)).to(cuda)
+    tup = list(to_tuple(nb, cuda)); tup[7] = tai
+    res = prod(*tup)
+    n = res.rm_obj_dists.size(0)
+    assert res.rm_obj_labels.shape == (n,) and int(res.rm_obj_labels.min()) >= 0
+    assert res.rel_labels.size(1) == 4 and res.rel_dists.shape == (res.rel_labels.size(0), 51)
+    assert int(res.rel_labels[:, 1].max()) < n and int(res.rel_labels[:, 2].max()) < n
+    F = torch.nn.functional
+    loss = F.cross_entropy(res.rm_obj_dists, res.rm_obj_labels) + F.cross_entropy(res.rel_dists, res.rel_labels[:, -1])
+    loss.backward()
+    assert torch.isfinite(loss)
+    g = prod.context.decoder_rnn.input_linearity.weight.grad
+    assert g is not None and torch.isfinite(g).all() and float(g.abs().max()) > 0

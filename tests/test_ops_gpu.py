@@ -299,3 +299,52 @@ def test_highway_lstm_eval_and_drop_in_symbol_vs_reference_kernel(cuda):
     for t in range(T):
         cov = sum(1 for l in lengths if l > t)
         np.testing.assert_allclose(g1[:, t, :cov].cpu().numpy(), g2[:, t, :cov].cpu().numpy(), rtol=1e-4, atol=2e-5)
+
+
+# ------------------------------------------------------------------------------- train-time assignments
+def _synthetic_detections(rng, num_im=3, per_im=30, gt_per_im=8):
+    gt_boxes, gt_classes, gt_rels, rois, labels, im_inds = [], [], [], [], [], []
+    for im in range(num_im):
+        gb = rand_boxes(rng, gt_per_im, lo=40, hi=250)
+        gc = rng.randint(1, 151, gt_per_im)
+        gt_boxes.append(gb); gt_classes.append(np.stack([np.full(gt_per_im, im), gc], 1))
+        pairs = [(a, b) for a in range(gt_per_im) for b in range(gt_per_im) if a != b]
+        sel = rng.choice(len(pairs), 6, replace=False)
+        gt_rels.append(np.array([[im, pairs[k][0], pairs[k][1], rng.randint(1, 51)] for k in sel]))
+        # detections: jittered copies of GT boxes (matching labels) + random boxes (label 0)
+        src = rng.randint(0, gt_per_im, per_im // 2)
+        jit = gb[src] + rng.uniform(-6, 6, (per_im // 2, 4)).astype(np.float32)
+        rnd = rand_boxes(rng, per_im - per_im // 2, lo=30, hi=200)
+        rois.append(np.concatenate([jit, rnd]).astype(np.float32))
+        labels.append(np.concatenate([gc[src], np.zeros(per_im - per_im // 2, np.int64)]))
+        im_inds.append(np.full(per_im, im))
+    return (np.concatenate(im_inds), np.concatenate(rois), np.concatenate(labels).astype(np.int64),
+            np.concatenate(gt_boxes).astype(np.float32), np.concatenate(gt_classes).astype(np.int64),
+            np.concatenate(gt_rels).astype(np.int64))
+
+
+def test_rel_assignments_identical_to_oracle(cuda):
+    from lib.fpn.proposal_assignments.rel_assignments import rel_assignments
+    from oracle import host
+    rng = np.random.RandomState(21)
+    im_inds, rois, labels, gt_boxes, gt_classes, gt_rels = _synthetic_detections(rng)
+    for nspg, fno in [(1, True), (4, False)]:
+        got = rel_assignments(torch.from_numpy(im_inds).to(cuda), torch.from_numpy(rois).to(cuda),
+                              torch.from_numpy(labels).to(cuda), torch.from_numpy(gt_boxes).to(cuda),
+                              torch.from_numpy(gt_classes).to(cuda), torch.from_numpy(gt_rels).to(cuda), 0,
+                              num_sample_per_gt=nspg, filter_non_overlap=fno, rng=np.random.RandomState(5))
+        exp = host.rel_assignments(im_inds, rois, labels, gt_boxes, gt_classes, gt_rels, 0, np.random.RandomState(5),
+                                   num_sample_per_gt=nspg, filter_non_overlap=fno)
+        assert got.dtype == torch.int64 and np.array_equal(got.cpu().numpy(), exp)
+
+
+def test_proposal_assignments_det_identical_to_oracle(cuda):
+    from lib.fpn.proposal_assignments.proposal_assignments_det import proposal_assignments_det
+    from oracle import host
+    rng = np.random.RandomState(22)
+    im_inds, rois, labels, gt_boxes, gt_classes, gt_rels = _synthetic_detections(rng, num_im=2, per_im=400, gt_per_im=10)
+    rois5 = np.concatenate([im_inds[:, None].astype(np.float32), rois], 1)
+    r, l, t = proposal_assignments_det(torch.from_numpy(rois5).to(cuda), torch.from_numpy(gt_boxes).to(cuda),
+                                       torch.from_numpy(gt_classes).to(cuda), 0, rng=np.random.RandomState(9))
+    er, el, et = host.proposal_assignments_det(rois5, gt_boxes, gt_classes, 0, np.random.RandomState(9))
+    assert np.array_equal(r.cpu().numpy(), er) and np.array_equal(l.cpu().numpy(), el) and np.array_equal(t.cpu().numpy(), et)
