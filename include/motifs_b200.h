@@ -156,6 +156,10 @@ int mb200_split_transpose_bf16(const float* src, int rows, int cols, long long l
 int mb200_conv_weight_split(const float* w_oihw, int O, int I, int Ip, void* hi, void* lo, cudaStream_t stream);
 int mb200_im2col3_split(const float* x_nchw, int B, int H, int W, void* hi, void* lo, cudaStream_t stream);
 int mb200_stem_weight_split(const float* w_oihw, int O, void* hi, void* lo, cudaStream_t stream);
+/* VGG stem conv1_1 (3->64, 3x3, pad 1) + bias (+ReLU): fp32 NCHW image -> NHWC bf16 pair, exact fp32
+ * direct convolution (replaces the first nn.Conv2d of lib/object_detector.py:110-127). Cout must be 64. */
+int mb200_conv3x3_stem_split(const float* x_nchw, const float* w_oihw, const float* bias, int B, int H, int W,
+                             int Cout, int relu, void* yhi, void* ylo, cudaStream_t stream);
 int mb200_maxpool2_nhwc_split(const void* xhi, const void* xlo, int B, int H, int W, int C, void* yhi, void* ylo,
                               cudaStream_t stream);
 

@@ -14,6 +14,10 @@ from lib.draw_rectangles.draw_rectangles import draw_union_boxes_cuda
 from lib.fpn.roi_align.functions.roi_align import RoIAlignFunction, roi_align_from_nhwc
 
 
+import os
+_MASKCONV_CHANNELS_LAST = os.environ.get("MOTIFS_MASKCONV_CL", "0") == "1"
+
+
 def union_rois_and_pairs(rois, union_inds):
     """rois [N,5], union_inds [R,2] int64 -> (union rois [R,5], pair boxes [R,8]) in one kernel
     (get_union_boxes.py:82-87 and the gather of :47)."""
@@ -67,6 +71,12 @@ class UnionBoxesAndFeats(Module):
         rects = draw_union_boxes_cuda(pair_boxes, self.pooling_size * 4 - 1, offset=0.5)
         # The mask conv net (7x7 s2 + 3x3) still runs on cuDNN this round; TF32 is
         # switched off so it stays inside the fp32 parity bar (TF32 alone costs ~1e-3 here).
+        if _MASKCONV_CHANNELS_LAST:
+            # NHWC kernels for the cuDNN conv / BN / pool of this branch (layout only; same arithmetic)
+            if not getattr(self, "_cl_done", False):
+                self.conv.to(memory_format=torch.channels_last)
+                self._cl_done = True
+            rects = rects.contiguous(memory_format=torch.channels_last)
         with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
             conv_out = self.conv(rects)
         if self.concat:

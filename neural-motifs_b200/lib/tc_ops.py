@@ -279,15 +279,24 @@ def vgg_features_forward(x, convs, want_last_split=False):
     B, _, H, W = x.shape
     dev = x.device
     lib = _c.load()
-    # stem: explicit im2col (K = 27 -> 64) + plain GEMM with fused bias/ReLU, output NHWC pair
-    a_hi = torch.empty(B * H * W, 64, dtype=torch.bfloat16, device=dev); a_lo = torch.empty_like(a_hi)
-    with torch.cuda.device(dev):
-        _c.check(lib.mb200_im2col3_split(_c.ptr(x), B, H, W, _c.ptr(a_hi), _c.ptr(a_lo), _c.cur_stream()), "im2col3")
-    w0 = _conv_weight_split(convs[0].weight)
-    cur = gemm(SplitMat(a_hi, a_lo, B * H * W, 27, 64), w0, bias=convs[0].bias.detach(), relu=True,
-               want_f32=False, want_split=True)
     C = convs[0].weight.size(0)
-    xs = (cur.hi.view(B, H, W, C), cur.lo.view(B, H, W, C))
+    if C == 64 and convs[0].weight.size(1) == 3:
+        # stem: exact-fp32 direct convolution straight to the NHWC bf16 pair (csrc/stem.cu)
+        xh = torch.empty(B, H, W, C, dtype=torch.bfloat16, device=dev); xl = torch.empty_like(xh)
+        w0 = convs[0].weight.detach().contiguous()
+        with torch.cuda.device(dev):
+            _c.check(lib.mb200_conv3x3_stem_split(_c.ptr(x), _c.ptr(w0), _c.ptr(convs[0].bias.detach()), B, H, W, C, 1,
+                                                  _c.ptr(xh), _c.ptr(xl), _c.cur_stream()), "mb200_conv3x3_stem_split")
+        xs = (xh, xl)
+    else:
+        # generic stem: explicit im2col (K = 27 -> 64) + plain GEMM with fused bias/ReLU
+        a_hi = torch.empty(B * H * W, 64, dtype=torch.bfloat16, device=dev); a_lo = torch.empty_like(a_hi)
+        with torch.cuda.device(dev):
+            _c.check(lib.mb200_im2col3_split(_c.ptr(x), B, H, W, _c.ptr(a_hi), _c.ptr(a_lo), _c.cur_stream()), "im2col3")
+        w0 = _conv_weight_split(convs[0].weight)
+        cur = gemm(SplitMat(a_hi, a_lo, B * H * W, 27, 64), w0, bias=convs[0].bias.detach(), relu=True,
+                   want_f32=False, want_split=True)
+        xs = (cur.hi.view(B, H, W, C), cur.lo.view(B, H, W, C))
     ci = 1
     out = None
     for li, v in enumerate(VGG16_CFG[1:], start=1):

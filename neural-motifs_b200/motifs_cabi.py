@@ -45,6 +45,7 @@ SIGNATURES = {
     "mb200_conv_weight_split": (c_int, [P, c_int, c_int, c_int, P, P, P]),
     "mb200_im2col3_split": (c_int, [P, c_int, c_int, c_int, P, P, P]),
     "mb200_stem_weight_split": (c_int, [P, c_int, P, P, P]),
+    "mb200_conv3x3_stem_split": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, P, P, P]),
     "mb200_maxpool2_nhwc_split": (c_int, [P, P, c_int, c_int, c_int, c_int, P, P, P]),
     "mb200_sgd_momentum_clip": (c_int, [P, P, P, c_longlong, c_float, c_float, c_float, P, c_float, c_int, c_int, P]),
     "mb200_sgemm": (c_int, [c_int, c_int, c_int, c_int, c_int, c_float, P, c_int, P, c_int, c_float, P, c_int, P]),

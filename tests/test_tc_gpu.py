@@ -121,3 +121,18 @@ def test_flat_sgd_matches_torch_sgd_with_clip(cuda):
         for p, q in zip(a, b):
             assert torch.allclose(p, q, rtol=1e-5, atol=1e-6), float((p - q).abs().max())
             assert float(p.grad.abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("B,H,W", [(1, 5, 7), (2, 33, 70), (1, 64, 96)])
+def test_stem_conv_vs_fp64(cuda, B, H, W):
+    """csrc/stem.cu: conv1_1 (3->64) + bias + ReLU, exact fp32 FMAs; output is the NHWC bf16 pair."""
+    import motifs_cabi as C
+    torch.manual_seed(H)
+    conv = torch.nn.Conv2d(3, 64, 3, padding=1).to(cuda)
+    x = torch.randn(B, 3, H, W, device=cuda)
+    yh = torch.empty(B, H, W, 64, dtype=torch.bfloat16, device=cuda); yl = torch.empty_like(yh)
+    C.check(C.load().mb200_conv3x3_stem_split(C.ptr(x), C.ptr(conv.weight.detach().contiguous()), C.ptr(conv.bias.detach()),
+                                              B, H, W, 64, 1, C.ptr(yh), C.ptr(yl), C.cur_stream()), "stem")
+    ref = torch.nn.functional.conv2d(x.double(), conv.weight.double(), conv.bias.double(), padding=1).clamp_min(0)
+    got = (yh.float() + yl.float()).permute(0, 3, 1, 2)
+    assert relerr(got, ref) < 2e-5, relerr(got, ref)      # bounded by the bf16-pair output format (2^-17)
