@@ -163,6 +163,13 @@ int mb200_conv3x3_stem_split(const float* x_nchw, const float* w_oihw, const flo
 int mb200_maxpool2_nhwc_split(const void* xhi, const void* xlo, int B, int H, int W, int C, void* yhi, void* ylo,
                               cudaStream_t stream);
 
+/* 3x3 / stride 2 / pad 1 max-pool on [planes,H,W] fp32 (nn.MaxPool2d(3,2,1) of lib/get_union_boxes.py:34):
+ * forward stores the arg-max (0..8) per output, backward is a deterministic gather. */
+int mb200_maxpool3s2_forward(const float* x, long long planes, int H, int W, float* y, unsigned char* argmax,
+                             cudaStream_t stream);
+int mb200_maxpool3s2_backward(const float* grad_y, const unsigned char* argmax, long long planes, int H, int W,
+                              float* grad_x, cudaStream_t stream);
+
 /* Fused clip + weight-decay + momentum SGD over a flat fp32 buffer (replaces the caller-side
  * clip_grad_norm + optim.SGD.step of models/train_rels.py:145-150). total_norm_dev: device scalar with
  * the global gradient norm, or NULL for no clipping. Pointers 16-byte aligned. */

@@ -40,6 +40,37 @@ def union_boxes(fmap, rois, union_inds, pooling_size=14, stride=16):
     return RoIAlignFunction(pooling_size, pooling_size, spatial_scale=1 / stride)(fmap, u)
 
 
+class _MaxPool3s2(torch.autograd.Function):
+    """nn.MaxPool2d(kernel_size=3, stride=2, padding=1) on NCHW fp32 over csrc/pool.cu."""
+
+    @staticmethod
+    def forward(ctx, x):
+        _c.require_cuda(x)
+        x = x.contiguous()
+        N, C, H, W = x.shape
+        Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+        y = torch.empty(N, C, Ho, Wo, device=x.device, dtype=torch.float32)
+        arg = torch.empty(N, C, Ho, Wo, device=x.device, dtype=torch.uint8)
+        with torch.cuda.device(x.device):
+            _c.check(_c.load().mb200_maxpool3s2_forward(_c.ptr(x), N * C, H, W, _c.ptr(y), _c.ptr(arg), _c.cur_stream()),
+                     "mb200_maxpool3s2_forward")
+        ctx.save_for_backward(arg)
+        ctx.hw = (H, W)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        (arg,) = ctx.saved_tensors
+        H, W = ctx.hw
+        N, C = arg.shape[:2]
+        gy = gy.contiguous()
+        gx = torch.empty(N, C, H, W, device=gy.device, dtype=torch.float32)
+        with torch.cuda.device(gy.device):
+            _c.check(_c.load().mb200_maxpool3s2_backward(_c.ptr(gy), _c.ptr(arg), N * C, H, W, _c.ptr(gx), _c.cur_stream()),
+                     "mb200_maxpool3s2_backward")
+        return gx
+
+
 class UnionBoxesAndFeats(Module):
     def __init__(self, pooling_size=7, stride=16, dim=256, concat=False, use_feats=True):
         super().__init__()
@@ -78,7 +109,13 @@ class UnionBoxesAndFeats(Module):
                 self._cl_done = True
             rects = rects.contiguous(memory_format=torch.channels_last)
         with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
-            conv_out = self.conv(rects)
+            conv_out = rects
+            for m in self.conv:
+                if isinstance(m, nn.MaxPool2d) and m.kernel_size == 3 and m.stride == 2 and m.padding == 1 \
+                        and not _MASKCONV_CHANNELS_LAST:
+                    conv_out = _MaxPool3s2.apply(conv_out)
+                else:
+                    conv_out = m(conv_out)
         if self.concat:
             return torch.cat((union_pools, conv_out), 1)
         return union_pools + conv_out

@@ -47,6 +47,8 @@ SIGNATURES = {
     "mb200_stem_weight_split": (c_int, [P, c_int, P, P, P]),
     "mb200_conv3x3_stem_split": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, P, P, P]),
     "mb200_maxpool2_nhwc_split": (c_int, [P, P, c_int, c_int, c_int, c_int, P, P, P]),
+    "mb200_maxpool3s2_forward": (c_int, [P, c_longlong, c_int, c_int, P, P, P]),
+    "mb200_maxpool3s2_backward": (c_int, [P, P, c_longlong, c_int, c_int, P, P]),
     "mb200_sgd_momentum_clip": (c_int, [P, P, P, c_longlong, c_float, c_float, c_float, P, c_float, c_int, c_int, P]),
     "mb200_sgemm": (c_int, [c_int, c_int, c_int, c_int, c_int, c_float, P, c_int, P, c_int, c_float, P, c_int, P]),
 }

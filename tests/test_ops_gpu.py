@@ -348,3 +348,17 @@ def test_proposal_assignments_det_identical_to_oracle(cuda):
                                        torch.from_numpy(gt_classes).to(cuda), 0, rng=np.random.RandomState(9))
     er, el, et = host.proposal_assignments_det(rois5, gt_boxes, gt_classes, 0, np.random.RandomState(9))
     assert np.array_equal(r.cpu().numpy(), er) and np.array_equal(l.cpu().numpy(), el) and np.array_equal(t.cpu().numpy(), et)
+
+
+def test_maxpool3s2_matches_torch(cuda):
+    from lib.get_union_boxes import _MaxPool3s2
+    torch.manual_seed(0)
+    for shape in [(3, 5, 14, 14), (2, 4, 27, 27), (1, 2, 7, 9)]:
+        x = torch.randn(*shape, device=cuda).clamp_min(0).requires_grad_(True)   # post-ReLU: many tied zeros
+        y = _MaxPool3s2.apply(x)
+        ref_in = x.detach().clone().requires_grad_(True)
+        ref = torch.nn.functional.max_pool2d(ref_in, 3, 2, 1)
+        assert torch.equal(y, ref)
+        g = torch.randn_like(ref)
+        y.backward(g); ref.backward(g)
+        assert torch.equal(x.grad, ref_in.grad)
