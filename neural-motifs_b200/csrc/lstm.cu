@@ -139,7 +139,25 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_fwd_kernel(FwdArgs a) {
         }
         float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
         const float* hrow = hs + (size_t)rc * ldh;
-        for (int k = ks; k < H; k += KS) {
+        // 4 k-steps per iteration, all 24 shared-memory loads issued before the FMAs (ncu: the
+        // non-unrolled loop was LDS-latency bound); H / KS is a multiple of 4 (KS <= 32, H % 128 == 0) or
+        // the tail loop finishes it.
+        int k = ks;
+        for (; k + 3 * KS < H; k += 4 * KS) {
+          float hv[4], wv[4][5];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            hv[q] = hrow[k + q * KS];
+            const float* w = Ws + (size_t)(k + q * KS) * 5 * kUJ + u;
+#pragma unroll
+            for (int g = 0; g < 5; ++g) wv[q][g] = w[g * kUJ];
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int g = 0; g < 5; ++g) acc[g] = fmaf(hv[q], wv[q][g], acc[g]);
+        }
+        for (; k < H; k += KS) {
           const float hv = hrow[k];
           const float* w = Ws + (size_t)k * 5 * kUJ + u;
 #pragma unroll
@@ -203,6 +221,7 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_bwd_kernel(BwdArgs a) {
   float* Ws = smem;                          // [kUJ][5H]: rows k0..k0+3 of W_h
   float* gs = Ws + (size_t)kUJ * H5;         // [kBTb][ldg]
   int* lens = (int*)(gs + (size_t)kBTb * ldg);
+  __shared__ float red[(kThreads / 32) * kBTb * kUJ];
   const int tid = threadIdx.x;
   const int j0 = blockIdx.x * kUJ;
   const int u = tid / kTPU;
@@ -266,18 +285,50 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_bwd_kernel(BwdArgs a) {
           if (r < rows) *(float4*)(gs + (size_t)r * ldg + 4 * v0) = x[r];
       }
       __syncthreads();
-      const int KS = pick_ks(rows);
-      const int ks = t64 % KS, slot = t64 / KS, nslots = kTPU / KS;
-      const int iters = (rows + nslots - 1) / nslots;
-      const float* w = Ws + (size_t)u * H5;
-      for (int m = 0; m < iters; ++m) {
-        const int r = slot + m * nslots;
-        const bool active = r < rows;
-        const float* grow = gs + (size_t)(active ? r : 0) * ldg;
-        float acc = 0.f;
-        for (int k = ks; k < H5; k += KS) acc = fmaf(grow[k], w[k], acc);
-        for (int o = KS >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if (active && ks == 0) hg[(size_t)(b0 + r) * H + j0 + u] = acc;
+      // All 256 threads split K = 5H; each keeps a [rows][4 units] accumulator tile, so a k-step costs
+      // rows + 4 shared loads for 4*rows FMAs (ncu on the first version: one LDS pair per FMA in a
+      // non-unrolled loop, 50 % of all stall samples). Then warp shuffles + one shared round reduce.
+      float acc[kBTb][kUJ];
+#pragma unroll
+      for (int r = 0; r < kBTb; ++r)
+#pragma unroll
+        for (int q = 0; q < kUJ; ++q) acc[r][q] = 0.f;
+      for (int k = tid; k < H5; k += kThreads) {
+        float wv[kUJ], gv[kBTb];
+#pragma unroll
+        for (int q = 0; q < kUJ; ++q) wv[q] = Ws[(size_t)q * H5 + k];
+#pragma unroll
+        for (int r = 0; r < kBTb; ++r) gv[r] = (r < rows) ? gs[(size_t)r * ldg + k] : 0.f;
+#pragma unroll
+        for (int r = 0; r < kBTb; ++r)
+#pragma unroll
+          for (int q = 0; q < kUJ; ++q) acc[r][q] = fmaf(gv[r], wv[q], acc[r][q]);
+      }
+#pragma unroll
+      for (int r = 0; r < kBTb; ++r)
+        if (r < rows) {                       // uniform across the CTA
+#pragma unroll
+          for (int q = 0; q < kUJ; ++q) {
+            float v = acc[r][q];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            acc[r][q] = v;
+          }
+        }
+      const int lane_ = tid & 31, warp_ = tid >> 5;
+      if (lane_ == 0) {
+#pragma unroll
+        for (int r = 0; r < kBTb; ++r)
+#pragma unroll
+          for (int q = 0; q < kUJ; ++q) red[(warp_ * kBTb + r) * kUJ + q] = acc[r][q];
+      }
+      __syncthreads();
+      if (tid < rows * kUJ) {
+        const int r = tid / kUJ, q = tid - r * kUJ;
+        float v = 0.f;
+#pragma unroll
+        for (int wq = 0; wq < kThreads / 32; ++wq) v += red[(wq * kBTb + r) * kUJ + q];
+        hg[(size_t)(b0 + r) * H + j0 + q] = v;
       }
       __syncthreads();
     }
