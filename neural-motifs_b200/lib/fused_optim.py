@@ -14,7 +14,7 @@ from lib import tc_ops
 
 
 class FlatGroup(object):
-    def __init__(self, params, lr):
+    def __init__(self, params, lr, chunk_bytes=128 << 20):
         self.params = params
         self.lr = lr
         dev = params[0].device
@@ -32,16 +32,49 @@ class FlatGroup(object):
                 view.copy_(p.data)
                 p.data = view
                 p.grad = self.flat_g[o:o + p.numel()].view_as(p)
+        # communication chunks: contiguous runs of whole parameters, ~chunk_bytes each. A chunk is
+        # all-reduced as soon as autograd has produced the gradient of every parameter in it.
+        self.chunks, cur, start, size = [], [], 0, 0
+        for p, o in zip(params, offs):
+            n = (p.numel() + 3) // 4 * 4
+            if cur and size + n * 4 > chunk_bytes:
+                self.chunks.append((start, o, cur))
+                cur, start, size = [], o, 0
+            cur.append(p)
+            size += n * 4
+        if cur:
+            self.chunks.append((start, self.n, cur))
 
 
 class FlatSGD(object):
     """groups: list of (params, lr). momentum / weight_decay / max_norm shared (train_rels.py:66,145)."""
 
-    def __init__(self, groups, momentum=0.9, weight_decay=1e-4, max_norm=5.0):
-        self.groups = [FlatGroup([p for p in ps if p.requires_grad], lr) for ps, lr in groups if len(ps)]
+    def __init__(self, groups, momentum=0.9, weight_decay=1e-4, max_norm=5.0, overlap_comm=True, chunk_bytes=128 << 20):
+        self.groups = [FlatGroup([p for p in ps if p.requires_grad], lr, chunk_bytes) for ps, lr in groups if len(ps)]
         self.momentum, self.weight_decay, self.max_norm = momentum, weight_decay, max_norm
         self.steps = 0
         tc_ops.bump_weight_epoch()       # storages moved
+        self._works = []
+        self._pending = {}
+        self._distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        if self._distributed and overlap_comm:
+            # overlap the gradient all-reduce with backward: one hook per parameter counts down its
+            # chunk; the last one launches the chunk's all-reduce (NCCL stream) while autograd keeps going
+            for g in self.groups:
+                for ci, (a, b, ps) in enumerate(g.chunks):
+                    for p in ps:
+                        p.register_post_accumulate_grad_hook(self._make_hook(g, ci))
+        self._overlap = self._distributed and overlap_comm
+
+    def _make_hook(self, group, ci):
+        def hook(param):
+            key = (id(group), ci)
+            left = self._pending.get(key, len(group.chunks[ci][2])) - 1
+            self._pending[key] = left
+            if left == 0:
+                a, b, _ = group.chunks[ci]
+                self._works.append((dist.all_reduce(group.flat_g[a:b], op=dist.ReduceOp.SUM, async_op=True), group, a, b))
+        return hook
 
     def zero_grad(self, set_to_none=False):
         """Gradients are zeroed by the fused step itself; kept for API symmetry (never set to None:
@@ -51,11 +84,26 @@ class FlatSGD(object):
                 g.flat_g.zero_()
 
     def all_reduce_grads(self):
-        """Data-parallel average: ONE all-reduce per group on the flat gradient buffer."""
-        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        """Data-parallel average of the flat gradient buffers. With overlap the chunk all-reduces were
+        launched from the autograd hooks during backward; here they are only waited for (and any chunk
+        whose parameters received no gradient this step is reduced now)."""
+        if not self._distributed:
+            return
+        inv = 1.0 / dist.get_world_size()
+        if self._overlap:
+            done = set()
+            for w, g, a, b in self._works:
+                w.wait()
+                done.add((id(g), a))
+            for g in self.groups:
+                for (a, b, _) in g.chunks:
+                    if (id(g), a) not in done:
+                        dist.all_reduce(g.flat_g[a:b], op=dist.ReduceOp.SUM)
+            self._works, self._pending = [], {}
+            for g in self.groups:
+                g.flat_g.mul_(inv)
             return
         works = [dist.all_reduce(g.flat_g, op=dist.ReduceOp.SUM, async_op=True) for g in self.groups]
-        inv = 1.0 / dist.get_world_size()
         for w, g in zip(works, self.groups):
             w.wait()
             g.flat_g.mul_(inv)

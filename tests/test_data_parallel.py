@@ -43,3 +43,45 @@ def test_grad_all_reduce_gloo_world2():
         assert torch.equal(a, b)
         expect = (1 + 2) / 2 * (i + 1) if i != 2 else 1 * (i + 1) / 2
         assert torch.allclose(a, torch.full_like(a, expect))
+
+
+def _worker_flat(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "neural-motifs_b200"))
+    from lib.data_parallel import init_from_env
+    from lib.fused_optim import FlatSGD
+    init_from_env("gloo")
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(16, 64), torch.nn.ReLU(), torch.nn.Linear(64, 32), torch.nn.ReLU(),
+                              torch.nn.Linear(32, 4))
+    unused = torch.nn.Parameter(torch.zeros(10))            # never receives a gradient
+    params = list(net.parameters()) + [unused]
+    opt = FlatSGD([(params[:2], 0.1), (params[2:], 0.01)], overlap_comm=True, chunk_bytes=4096)
+    assert sum(len(g.chunks) for g in opt.groups) >= 3
+    opt.zero_grad()
+    torch.manual_seed(100 + rank)                           # different data per rank
+    x = torch.randn(8, 16)
+    net(x).pow(2).mean().backward()                         # hooks launch the chunk all-reduces
+    local = [p.grad.clone() for p in params]                # (already being reduced in place)
+    opt.all_reduce_grads()
+    out[rank] = [p.grad.clone() for p in params]
+    # reference: recompute this rank's own gradient without hooks
+    ref = torch.nn.Sequential(torch.nn.Linear(16, 64), torch.nn.ReLU(), torch.nn.Linear(64, 32), torch.nn.ReLU(),
+                              torch.nn.Linear(32, 4))
+    ref.load_state_dict(net.state_dict())
+    ref(x).pow(2).mean().backward()
+    out[10 + rank] = [p.grad.clone() for p in ref.parameters()]
+    dist.destroy_process_group()
+
+
+def test_flat_sgd_overlapped_all_reduce_gloo_world2():
+    """lib/fused_optim.FlatSGD: per-chunk all-reduce launched from autograd hooks == plain average."""
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker_flat, args=(2, _free_port(), out), nprocs=2, join=True)
+    for i in range(6):
+        avg = (out[10][i] + out[11][i]) / 2
+        assert torch.allclose(out[0][i], avg, atol=1e-7) and torch.allclose(out[1][i], avg, atol=1e-7)
+    assert float(out[0][6].abs().max()) == 0.0
