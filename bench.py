@@ -154,6 +154,8 @@ def run_b200(args):
     from lib.data_parallel import init_from_env
     from dataloaders.synthetic import make_numpy_batch, SyntheticBlob
 
+    if "MOTIFS_KEEP_NCCL_DEBUG" not in os.environ:
+        os.environ["NCCL_DEBUG"] = "WARN"          # NCCL's version banner would otherwise land on stdout before the JSON line
     rank, world, local = init_from_env("nccl")
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py (impl b200) needs a CUDA device; there is no CPU fallback")
@@ -219,6 +221,9 @@ def run_b200(args):
     peak_tf = float(pk.get("bf16_tflops_sustained", pk["bf16_tflops"]))
     achieved = flops / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
 
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
     imgs = BATCH_PER_GPU * world * args.steps

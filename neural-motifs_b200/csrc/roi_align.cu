@@ -245,7 +245,7 @@ roi_align_fwd_nchw_kernel(const float* __restrict__ feat, const float* __restric
 // Pipeline variant: the backbone epilogue leaves conv5_3 as NHWC fp32; pooled features come out
 // bin-major / channel-minor, the K order the fc6 tensor-core GEMM consumes. One CTA per
 // (roi, 128-channel chunk): a warp owns one bin at a time, each lane 4 consecutive channels.
-constexpr int kChunkNHWC = 128;
+constexpr int kChunkNHWC = 256;    // channels per CTA: each lane owns two groups of 4 channels (8 x 16-byte loads per bin)
 constexpr int kNhwcStageArea = 96;       // windows up to 96 px are staged: 96 * 512 B = 48 KB
 constexpr bool kNhwcUseStaging = false;  // measured on B200: L1 already serves the re-reads (39 us vs 49 us staged)
 // CHW == false: out [N, bins, C] (bin-major).  CHW == true: out [N, C, bins] — the reference's
@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(kThreads)
 roi_align_fwd_nhwc_kernel(const float* __restrict__ feat, const float* __restrict__ boxes,
                           int num_boxes, int batch, int H, int W, int PH, int PW, int C,
                           float extrap, float* __restrict__ out) {
-  extern __shared__ __align__(16) float s_tile[];          // CHW only: [128][bins]
+  extern __shared__ __align__(16) float s_tile[];          // CHW only: [kChunkNHWC][bins]
   __shared__ AxisTab ty, tx;
   __shared__ RoiHead hd;
   __shared__ NhwcBin s_bin[kMaxBins];
@@ -271,6 +271,7 @@ roi_align_fwd_nhwc_kernel(const float* __restrict__ feat, const float* __restric
   const int c0 = blockIdx.y * kChunkNHWC;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int kWarps = kThreads / 32;
+  constexpr int kQ = kChunkNHWC / 128;                      // float4 groups per lane (128 channels each)
   const int bins = PH * PW;
   roi_preamble(boxes, n, batch, H, W, PH, PW, ty, tx, hd);
   for (int b = tid; b < bins; b += kThreads) {
@@ -284,37 +285,52 @@ roi_align_fwd_nhwc_kernel(const float* __restrict__ feat, const float* __restric
     s_bin[b] = d; s_binw[b] = w;
   }
   __syncthreads();
-  const int c = c0 + 4 * lane;
-  const bool lane_ok = c < C;
-  const float* img = feat + (size_t)(hd.bad_batch ? 0 : hd.b_in) * H * W * C + (lane_ok ? c : 0);
-  float* o = out + (size_t)n * bins * C + c;
+  const float* img0 = feat + (size_t)(hd.bad_batch ? 0 : hd.b_in) * H * W * C;
+  float* o0 = out + (size_t)n * bins * C;
 
-  auto sample = [&](int b) -> float4 {
+  // a warp owns whole bins; two bins are processed per iteration so that 2 x kQ x 4 = 16 independent
+  // 16-byte loads are in flight per lane (the CTA's duration, and with it the wave quantisation of
+  // short launches, is set by the number of dependent L2 round trips).
+  auto load_bin = [&](int b, float4 (&tl)[kQ], float4 (&tr)[kQ], float4 (&bl)[kQ], float4 (&br)[kQ]) {
     const NhwcBin d = s_bin[b];
-    const NhwcBinW w = s_binw[b];
-    const float4 tl = __ldg((const float4*)(img + d.o00)), tr = __ldg((const float4*)(img + d.o01));
-    const float4 bl = __ldg((const float4*)(img + d.o10)), br = __ldg((const float4*)(img + d.o11));
-    float4 v;
-    v.x = bilerp(tl.x, tr.x, bl.x, br.x, w.wx, w.wy); v.y = bilerp(tl.y, tr.y, bl.y, br.y, w.wx, w.wy);
-    v.z = bilerp(tl.z, tr.z, bl.z, br.z, w.wx, w.wy); v.w = bilerp(tl.w, tr.w, bl.w, br.w, w.wx, w.wy);
-    if (w.ok != 1) { const float e = (w.ok == 2) ? 0.f : extrap; v = make_float4(e, e, e, e); }
-    return v;
+#pragma unroll
+    for (int q = 0; q < kQ; ++q) {
+      const int c = c0 + q * 128 + 4 * lane;
+      const float* img = img0 + (c < C ? c : 0);
+      tl[q] = __ldg((const float4*)(img + d.o00)); tr[q] = __ldg((const float4*)(img + d.o01));
+      bl[q] = __ldg((const float4*)(img + d.o10)); br[q] = __ldg((const float4*)(img + d.o11));
+    }
   };
-  auto emit = [&](int b, const float4& v) {
-    if (CHW) {
-      float* t = s_tile + (size_t)(4 * lane) * bins + b;
-      t[0] = v.x; t[bins] = v.y; t[2 * bins] = v.z; t[3 * bins] = v.w;
-    } else if (lane_ok) {
-      *(float4*)(o + (size_t)b * C) = v;
+  auto finish_bin = [&](int b, const float4 (&tl)[kQ], const float4 (&tr)[kQ], const float4 (&bl)[kQ], const float4 (&br)[kQ]) {
+    const NhwcBinW w = s_binw[b];
+#pragma unroll
+    for (int q = 0; q < kQ; ++q) {
+      const int c = c0 + q * 128 + 4 * lane;
+      float4 v;
+      v.x = bilerp(tl[q].x, tr[q].x, bl[q].x, br[q].x, w.wx, w.wy); v.y = bilerp(tl[q].y, tr[q].y, bl[q].y, br[q].y, w.wx, w.wy);
+      v.z = bilerp(tl[q].z, tr[q].z, bl[q].z, br[q].z, w.wx, w.wy); v.w = bilerp(tl[q].w, tr[q].w, bl[q].w, br[q].w, w.wx, w.wy);
+      if (w.ok != 1) { const float e = (w.ok == 2) ? 0.f : extrap; v = make_float4(e, e, e, e); }
+      if (CHW) {
+        float* t = s_tile + (size_t)(q * 128 + 4 * lane) * bins + b;
+        t[0] = v.x; t[bins] = v.y; t[2 * bins] = v.z; t[3 * bins] = v.w;
+      } else if (c < C) {
+        *(float4*)(o0 + (size_t)b * C + c) = v;
+      }
     }
   };
   int b = warp;
-  for (; b + kWarps < bins; b += 2 * kWarps) {        // two bins per iteration: 8 loads in flight
-    const float4 v0 = sample(b);
-    const float4 v1 = sample(b + kWarps);
-    emit(b, v0); emit(b + kWarps, v1);
+  for (; b + kWarps < bins; b += 2 * kWarps) {
+    float4 tl0[kQ], tr0[kQ], bl0[kQ], br0[kQ], tl1[kQ], tr1[kQ], bl1[kQ], br1[kQ];
+    load_bin(b, tl0, tr0, bl0, br0);
+    load_bin(b + kWarps, tl1, tr1, bl1, br1);
+    finish_bin(b, tl0, tr0, bl0, br0);
+    finish_bin(b + kWarps, tl1, tr1, bl1, br1);
   }
-  if (b < bins) emit(b, sample(b));
+  if (b < bins) {
+    float4 tl0[kQ], tr0[kQ], bl0[kQ], br0[kQ];
+    load_bin(b, tl0, tr0, bl0, br0);
+    finish_bin(b, tl0, tr0, bl0, br0);
+  }
   if (CHW) {   // the chunk's [nc][bins] block is one contiguous run in global memory
     __syncthreads();
     const int nc = min(kChunkNHWC, C - c0);
@@ -518,13 +534,14 @@ static int roi_align_nhwc_launch(bool chw, const float* image_nhwc, const float*
   if (depth % 4 == 0 && ((((uintptr_t)image_nhwc) | ((uintptr_t)crops)) & 15) == 0) {
     dim3 grid(num_boxes, mb200_div_up(depth, kChunkNHWC));
     const size_t win = 0;
-    const size_t max_tile = (size_t)kChunkNHWC * kMaxBins * sizeof(float);
+    const size_t max_tile = 200 * 1024;      // opt-in ceiling; larger crops take the bin-major variant
     static bool attr_set = false;
     if (!attr_set) {
       MB200_CHECK(cudaFuncSetAttribute(roi_align_fwd_nhwc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)win));
       MB200_CHECK(cudaFuncSetAttribute(roi_align_fwd_nhwc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(win + max_tile)));
       attr_set = true;
     }
+    if (chw && (size_t)kChunkNHWC * bins * sizeof(float) > max_tile) return MB200_ERR_UNSUPPORTED;
     if (chw)
       roi_align_fwd_nhwc_kernel<true><<<grid, kThreads, win + (size_t)kChunkNHWC * bins * sizeof(float), stream>>>(
           image_nhwc, boxes_ptr, num_boxes, batch, image_height, image_width, crop_height, crop_width, depth,
