@@ -16,6 +16,7 @@ from lib.fpn.roi_align.functions.roi_align import RoIAlignFunction, roi_align_fr
 
 import os
 _MASKCONV_CHANNELS_LAST = os.environ.get("MOTIFS_MASKCONV_CL", "0") == "1"
+_CUDNN_BENCHMARK = os.environ.get("MOTIFS_CUDNN_BENCHMARK", "1") == "1"   # let cuDNN pick its fastest fp32 algorithm
 
 
 def union_rois_and_pairs(rois, union_inds):
@@ -108,7 +109,7 @@ class UnionBoxesAndFeats(Module):
                 self.conv.to(memory_format=torch.channels_last)
                 self._cl_done = True
             rects = rects.contiguous(memory_format=torch.channels_last)
-        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False, benchmark=_CUDNN_BENCHMARK):
             conv_out = rects
             for m in self.conv:
                 if isinstance(m, nn.MaxPool2d) and m.kernel_size == 3 and m.stride == 2 and m.padding == 1 \

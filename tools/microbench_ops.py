@@ -113,6 +113,10 @@ def bench_nms(res):
 
 
 def bench_lstm(res, quick):
+    """BASELINE configs[4]: H=512, L=2, B=256, T in {32,...}; plus the real SGCls shapes (B=6, T=20).
+    This library: the AlternatingHighwayLSTM module (tcgen05 hoisted projections + persistent recurrence),
+    forward and forward+backward. Reference: its kernels compiled unmodified (cuBLAS per step), forward."""
+    from torch.nn.utils.rnn import pack_padded_sequence
     from lib.lstm.highway_lstm_cuda.alternating_highway_lstm import AlternatingHighwayLSTM
     ref = ref_loader.ref_kernels()
     rows = []
@@ -121,27 +125,35 @@ def bench_lstm(res, quick):
         cfgs += [(128, 256, 712, 512, 2), (256, 256, 712, 512, 2)]
     for T, B, In, H, L in cfgs:
         torch.manual_seed(0)
-        m = AlternatingHighwayLSTM(In, H, L).to(dev)
-        x = torch.randn(T, B, In, device=dev)
+        m = AlternatingHighwayLSTM(In, H, L).to(dev).train()
+        x = torch.randn(T, B, In, device=dev, requires_grad=True)
         lengths = [T] * B
-        len_dev = torch.tensor(lengths, dtype=torch.int32, device=dev)
-        len_host = (ctypes.c_int * B)(*lengths)
         drop = torch.ones(L, B, H, device=dev)
-        h = torch.zeros(L, T + 1, B, H, device=dev); c = torch.zeros(L, T + 1, B, H, device=dev)
-        gates = torch.empty(L, T, B, 6 * H, device=dev)
-        lib = C.load()
-        w, bias = m.weight.detach(), m.bias.detach()
-        def mine():
-            C.check(lib.mb200_highway_lstm_forward(In, H, B, L, T, C.ptr(x), C.ptr(len_dev), C.ptr(h), C.ptr(c), C.ptr(w),
-                                                   C.ptr(bias), C.ptr(drop), C.ptr(gates), None, C.cur_stream()), "lstm")
-        t = timeit(mine, iters=5, warmup=2, flush=False)
+
+        def fwd():
+            with torch.no_grad():
+                m(pack_padded_sequence(x.detach(), lengths), dropout_weights=drop)
+
+        def fwd_bwd():
+            out, _ = m(pack_padded_sequence(x, lengths), dropout_weights=drop)
+            out.data.sum().backward()
+            m.zero_grad(set_to_none=True); x.grad = None
+        t_f = timeit(fwd, iters=5, warmup=2, flush=False)
+        t_fb = timeit(fwd_bwd, iters=5, warmup=2, flush=False)
         flops = sum(T * (2 * B * (In if l == 0 else H) * 6 * H + 2 * B * H * 5 * H) for l in range(L))
-        row = {"T": T, "B": B, "In": In, "H": H, "L": L, "fwd_us": t[0], "TFLOPs": flops / t[0] / 1e6}
+        row = {"T": T, "B": B, "In": In, "H": H, "L": L, "fwd_us": t_f[0], "fwd_bwd_us": t_fb[0],
+               "fwd_TFLOPs": flops / t_f[0] / 1e6}
         if ref is not None:
+            len_host = (ctypes.c_int * B)(*lengths)
+            h = torch.zeros(L, T + 1, B, H, device=dev); c = torch.zeros(L, T + 1, B, H, device=dev)
+            gates = torch.empty(L, T, B, 6 * H, device=dev)
             cublas = ctypes.CDLL("libcublas.so.12"); handle = ctypes.c_void_p(); cublas.cublasCreate_v2(ctypes.byref(handle))
             ti = torch.zeros(B, 6 * H, device=dev); th = torch.zeros(B, 5 * H, device=dev)
+            w, bias = m.weight.detach(), m.bias.detach()
+            xd = x.detach()
+
             def theirs():
-                ref.highway_lstm_forward_ongpu(In, H, B, L, T, C.ptr(x), len_host, C.ptr(h), C.ptr(c), C.ptr(ti), C.ptr(th),
+                ref.highway_lstm_forward_ongpu(In, H, B, L, T, C.ptr(xd), len_host, C.ptr(h), C.ptr(c), C.ptr(ti), C.ptr(th),
                                                C.ptr(w), C.ptr(bias), C.ptr(drop), C.ptr(gates), 1, C.cur_stream(), handle)
             row["ref_fwd_us"] = timeit(theirs, iters=3, warmup=1, flush=False)[0]
         rows.append(row)
