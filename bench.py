@@ -142,7 +142,7 @@ def train_step(model, optimizer, reducer=None, fwd_tuple=None, blob=None):
     loss.backward()
     optimizer.all_reduce_grads()
     optimizer.step()
-    return loss
+    return float(loss)          # the reference's train_batch reads the losses back every step (train_rels.py:151)
 
 
 # ------------------------------------------------------------------------------------------ b200 arm
@@ -207,7 +207,7 @@ def run_b200(args):
     losses = []
 
     def e2e_step(i):
-        losses.append(float(train_step(model, opt, reducer, blob=blobs[i % len(blobs)]).item()))
+        losses.append(train_step(model, opt, reducer, blob=blobs[i % len(blobs)]))
 
     for i in range(2):
         e2e_step(i)

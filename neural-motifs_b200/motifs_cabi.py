@@ -104,8 +104,9 @@ def ptr(t):
 
 
 def cur_stream():
+    """Raw cudaStream_t of torch's current stream on the current device (fast path: no Stream object)."""
     import torch
-    return c_void_p(torch.cuda.current_stream().cuda_stream)
+    return c_void_p(torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice()))
 
 
 def require_cuda(*tensors):
