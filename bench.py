@@ -190,16 +190,17 @@ def run_b200(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    W = max(args.warmup, 3)
+    W = max(args.warmup, 5)      # >= 3 required; 5 so that allocator, cuDNN autotuning and clocks are all settled
     sampler = ClockSampler(local)
-    sampler.start()            # started before the warm-up so that spawning nvidia-smi is not in the timed region
-    for i in range(W):
-        train_step(model, opt, reducer, fwd_tuple=resident[i % len(resident)])
-    # nvidia-smi takes ~1 s to initialise NVML (and pokes the driver while doing so): wait until it has
-    # delivered its first sample so that only its steady 10 Hz polling overlaps the timed region
+    sampler.start()
+    # nvidia-smi needs ~1 s to initialise NVML (and pokes the driver while doing so): wait for its first
+    # sample BEFORE the warm-up, so that the warm-up steps also bring the clocks back up from idle and
+    # only the steady 10 Hz polling overlaps the timed region.
     t_wait = time.time()
     while sampler.proc is not None and len(sampler.lines) == 0 and time.time() - t_wait < 8.0:
         time.sleep(0.05)
+    for i in range(W):
+        train_step(model, opt, reducer, fwd_tuple=resident[i % len(resident)])
     calls0 = motifs_cabi.LAUNCHER_CALLS
     ms_res = timed(lambda i: train_step(model, opt, reducer, fwd_tuple=resident[i % len(resident)]), args.steps)
     calls = motifs_cabi.LAUNCHER_CALLS - calls0
