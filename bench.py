@@ -201,6 +201,23 @@ def run_b200(args):
         time.sleep(0.05)
     for i in range(W):
         train_step(model, opt, reducer, fwd_tuple=resident[i % len(resident)])
+    # A fresh box keeps paging libraries in and autotuning for a while: keep warming up (untimed) until
+    # the step time has settled — three consecutive steps within 4 % of each other — or 40 extra steps.
+    recent, extra = [], 0
+    while extra < 40:
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        train_step(model, opt, reducer, fwd_tuple=resident[extra % len(resident)])
+        torch.cuda.synchronize(); recent.append(time.perf_counter() - t0); extra += 1
+        if len(recent) >= 3 and max(recent[-3:]) <= 1.04 * min(recent[-3:]) and \
+                (len(recent) < 6 or min(recent[-3:]) <= 1.04 * min(recent)):
+            break
+    if world > 1:       # every rank must leave the warm-up after the same number of steps
+        n_extra = torch.tensor([extra], device=dev)
+        dist.all_reduce(n_extra, op=dist.ReduceOp.MAX)
+        for i in range(int(n_extra.item()) - extra):
+            train_step(model, opt, reducer, fwd_tuple=resident[i % len(resident)])
+        extra = int(n_extra.item())
+    W += extra
     calls0 = motifs_cabi.LAUNCHER_CALLS
     ms_res = timed(lambda i: train_step(model, opt, reducer, fwd_tuple=resident[i % len(resident)]), args.steps)
     calls = motifs_cabi.LAUNCHER_CALLS - calls0
@@ -235,12 +252,13 @@ def run_b200(args):
     imgs = BATCH_PER_GPU * world * args.steps
     value = imgs / (ms_res * 1e-3)
     out = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": "MotifNet SGCls train_rels.py step, VGG16 backbone, batch 6x592x592 per GPU, "
                                "20 GT boxes + 15 GT rels per image (1536 rel triples), fwd+bwd+clip+SGD",
                    "global_batch": BATCH_PER_GPU * world, "parallelism": "dp%d" % world,
+                   "warmup_steps_run": W,
                    "arithmetic": "fp32 semantics: tcgen05 bf16x3 split-operand GEMM/conv, fp32 accumulate",
                    "l2": "per-step working set (1.7 GB params + activations) >> 126 MB L2; 4 rotating batches"},
         "e2e": {"value": imgs / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
