@@ -142,7 +142,7 @@ def train_step(model, optimizer, reducer=None, fwd_tuple=None, blob=None):
     loss.backward()
     optimizer.all_reduce_grads()
     optimizer.step()
-    return float(loss)          # the reference's train_batch reads the losses back every step (train_rels.py:151)
+    return float(loss.detach())  # the reference's train_batch reads the losses back every step (train_rels.py:151)
 
 
 # ------------------------------------------------------------------------------------------ b200 arm
@@ -274,7 +274,7 @@ def run_b200(args):
                      "backbone_conv_tflops": (sum(f for f, _ in conv) / (sum(t for _, t in conv) * 1e-3) / 1e12) if conv else None,
                      "note": "algorithmic fp32-equivalent FLOPs; the bf16x3 scheme issues 3 tensor-core MACs per "
                              "algorithmic MAC, so tensor-pipe busy fraction is ~3x frac",
-                     "traffic": None},
+                     "traffic": traffic_from_profile()},
         "clocks": clocks,
         "final_loss": losses[-1] if losses else None,
     }
@@ -283,6 +283,17 @@ def run_b200(args):
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(sample_images=2)
     print(json.dumps(out), flush=True)
+
+
+def traffic_from_profile():
+    """DRAM bytes per gemm_bf16x3_kernel launch (dram__bytes_read.sum + dram__bytes_write.sum averaged over
+    the launches of one training step) from the committed ncu capture under profiles/; None if absent."""
+    path = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["traffic_per_launch_bytes"])
+    except (OSError, KeyError, ValueError):
+        return None
 
 
 def roi_align_microbench(dev, pk, kind):
