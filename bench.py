@@ -180,11 +180,15 @@ def run_b200(args):
     def timed(fn, steps):
         barrier()
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        marks = []
         e0.record()
         for i in range(steps):
             fn(i)
+            ev = torch.cuda.Event(enable_timing=True); ev.record(); marks.append(ev)
         e1.record()
         barrier()
+        per_step = [a.elapsed_time(b) for a, b in zip([e0] + marks[:-1], marks)]
+        timed.last_per_step = per_step
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -202,14 +206,13 @@ def run_b200(args):
     for i in range(W):
         train_step(model, opt, reducer, fwd_tuple=resident[i % len(resident)])
     # A fresh box keeps paging libraries in and autotuning for a while: keep warming up (untimed) until
-    # the step time has settled — three consecutive steps within 4 % of each other — or 40 extra steps.
+    # the step time has settled — at least 12 extra steps and the last five within 3 % of each other and of the best — or 60 extra steps.
     recent, extra = [], 0
-    while extra < 40:
+    while extra < 60:
         torch.cuda.synchronize(); t0 = time.perf_counter()
         train_step(model, opt, reducer, fwd_tuple=resident[extra % len(resident)])
         torch.cuda.synchronize(); recent.append(time.perf_counter() - t0); extra += 1
-        if len(recent) >= 3 and max(recent[-3:]) <= 1.04 * min(recent[-3:]) and \
-                (len(recent) < 6 or min(recent[-3:]) <= 1.04 * min(recent)):
+        if len(recent) >= 12 and max(recent[-5:]) <= 1.03 * min(recent[-5:]) and min(recent[-5:]) <= 1.03 * min(recent):
             break
     if world > 1:       # every rank must leave the warm-up after the same number of steps
         n_extra = torch.tensor([extra], device=dev)
@@ -218,19 +221,42 @@ def run_b200(args):
             train_step(model, opt, reducer, fwd_tuple=resident[i % len(resident)])
         extra = int(n_extra.item())
     W += extra
+    # Python's cyclic GC pauses the host for tens of ms when a generation-2 pass lands in a step (seen as one
+    # 90 ms step among 21.7 ms ones): collect now, freeze what survived, and keep the collector off inside the
+    # timed regions (collected again between them) — the usual arrangement of a training loop.
+    import gc
+    gc_log = []
+    gc_t0 = [0.0]
+
+    def gc_cb(phase, info):
+        if phase == "start":
+            gc_t0[0] = time.perf_counter()
+        else:
+            gc_log.append((info.get("generation"), round((time.perf_counter() - gc_t0[0]) * 1e3, 2)))
+    gc.callbacks.append(gc_cb)
+    gc.collect(); gc.freeze(); gc.disable()
+    mem0 = torch.cuda.memory_stats(dev)
     calls0 = motifs_cabi.LAUNCHER_CALLS
     ms_res = timed(lambda i: train_step(model, opt, reducer, fwd_tuple=resident[i % len(resident)]), args.steps)
     calls = motifs_cabi.LAUNCHER_CALLS - calls0
+    steps_res = list(timed.last_per_step)
     # e2e: public API with host buffers; H2D of the batch and D2H of the loss every step
     losses = []
 
     def e2e_step(i):
         losses.append(train_step(model, opt, reducer, blob=blobs[i % len(blobs)]))
 
+    gc.collect()
     for i in range(2):
         e2e_step(i)
     ms_e2e = timed(e2e_step, args.steps)
     clocks = sampler.stop()
+    gc.enable(); gc.callbacks.remove(gc_cb)
+    mem1 = torch.cuda.memory_stats(dev)
+    host_notes = {"gc": "collector disabled inside the timed regions, gc.collect() between them",
+                  "gc_passes_ms": gc_log[-6:],
+                  "cuda_mallocs_in_timed_legs": int(mem1.get("num_device_alloc", 0) - mem0.get("num_device_alloc", 0)),
+                  "alloc_retries_in_timed_legs": int(mem1.get("num_alloc_retries", 0) - mem0.get("num_alloc_retries", 0))}
 
     # roofline leg: one extra profiled step, CUDA events around every tensor-core launch
     tc_ops.PROFILE = []
@@ -276,6 +302,8 @@ def run_b200(args):
                              "algorithmic MAC, so tensor-pipe busy fraction is ~3x frac",
                      "traffic": traffic_from_profile()},
         "clocks": clocks,
+        "host": host_notes,
+        "step_ms": {"value_leg": [round(t, 2) for t in steps_res], "e2e_leg": [round(t, 2) for t in timed.last_per_step]},
         "final_loss": losses[-1] if losses else None,
     }
     if world == 1:

@@ -170,6 +170,37 @@ int mb200_maxpool3s2_forward(const float* x, long long planes, int H, int W, flo
 int mb200_maxpool3s2_backward(const float* grad_y, const unsigned char* argmax, long long planes, int H, int W,
                               float* grad_x, cudaStream_t stream);
 
+/* ---- union-box mask branch (lib/get_union_boxes.py:28-37: conv7x7/s2 + ReLU + BN + maxpool3x3/s2 + conv3x3 +
+ * ReLU + BN on the [R,2,27,27] masks of draw_union_boxes), NHWC streaming kernels around mb200_gemm_bf16x3. ---- */
+/* im2col of the 7x7/s2/p3 stem over masks [R,2,S,S]: k = (ky*7+kx)*2 + c, 98 of 128 columns used.
+ * transposed == 0: (hi, lo) [R*Ho*Ho, 128]; transposed == 1: [128, Pp] with Pp >= R*Ho*Ho, Pp % 2 == 0. */
+int mb200_im2col7s2_split(const float* masks, int R, int S, int transposed, long long Pp, void* hi, void* lo,
+                          cudaStream_t stream);
+/* im2col of a 3x3/s1/p1 convolution over NHWC fp32 x [R,H,W,C]: k = (ky*3+kx)*C + c (the K order of
+ * mb200_conv_weight_split). transposed == 0: [R*H*W, 9C]; 1: [9C, Pp], Pp % 64 == 0, C % 32 == 0. */
+int mb200_im2col3_nhwc_split(const float* x, int R, int H, int W, int C, int transposed, long long Pp, void* hi,
+                             void* lo, cudaStream_t stream);
+/* nn.BatchNorm2d training statistics of x [P,C] (rows = N*H*W): two-pass mean / biased variance with double
+ * accumulation -> mean, invstd = rsqrt(var + eps); running_* (nullable) updated with `momentum` and the
+ * unbiased variance. sums: scratch of 4*C doubles. */
+int mb200_bn_stats(const float* x, long long P, int C, float eps, float momentum, double* sums, float* mean,
+                   float* invstd, float* running_mean, float* running_var, cudaStream_t stream);
+/* y = maxpool3x3/s2/p1(BN(x)) on NHWC [R,H,W,C] -> [R,Ho,Wo,C], arg-max code (0..8, first maximum) per output. */
+int mb200_bn_pool3s2_nhwc(const float* x, const float* mean, const float* invstd, const float* gamma, const float* beta,
+                          int R, int H, int W, int C, float* y, unsigned char* argmax, cudaStream_t stream);
+int mb200_unpool3s2_nhwc(const float* grad_y, const unsigned char* argmax, int R, int H, int W, int C, float* grad_x,
+                         cudaStream_t stream);
+/* out[R,C,HW] = BN(x[R,HW,C]) (+ addend[R,C,HW], nullable); HW <= 64. */
+int mb200_bn_nhwc_to_nchw(const float* x, const float* mean, const float* invstd, const float* gamma, const float* beta,
+                          const float* addend, int R, int HW, int C, float* out, cudaStream_t stream);
+int mb200_nchw_to_nhwc(const float* x, int R, int C, int HW, float* out, cudaStream_t stream);
+/* Backward of y = BN_train(x), x = ReLU(z): g = dL/dy [P,C]. sums[0:C] = sum g (dbeta), sums[C:2C] = sum g*xhat
+ * (dgamma), dz = dL/dz [P,C], dbias[C] = column sums of dz (doubles; all three overwritten). */
+int mb200_bn_relu_backward(const float* g, const float* x, const float* mean, const float* invstd, const float* gamma,
+                           long long P, int C, double* sums, float* dz, double* dbias, cudaStream_t stream);
+/* dx[R,H,W,C] from dcol [R*H*W, 9C] (adjoint of mb200_im2col3_nhwc_split, transposed == 0). */
+int mb200_col2im3_nhwc(const float* dcol, int R, int H, int W, int C, float* dx, cudaStream_t stream);
+
 /* Fused clip + weight-decay + momentum SGD over a flat fp32 buffer (replaces the caller-side
  * clip_grad_norm + optim.SGD.step of models/train_rels.py:145-150). total_norm_dev: device scalar with
  * the global gradient norm, or NULL for no clipping. Pointers 16-byte aligned. */

@@ -20,18 +20,33 @@ __global__ void sgd_momentum_clip_kernel(float* __restrict__ p, float* __restric
   const long long n4 = n >> 2;
   const long long stride = (long long)blockDim.x * gridDim.x;
   float4* p4 = (float4*)p; float4* g4 = (float4*)g; float4* b4 = (float4*)buf;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += stride) {
-    float4 pv = p4[i], gv = g4[i], bv = first_step ? make_float4(0.f, 0.f, 0.f, 0.f) : b4[i];
-    float* pp = (float*)&pv; float* gg = (float*)&gv; float* bb = (float*)&bv;
+  constexpr int U = 4;                     // 12 independent 16-byte loads in flight per thread before any store
+  for (long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x; i0 < n4; i0 += stride * U) {
+    float4 pv[U], gv[U], bv[U];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      float d = gg[k] * coef;
-      d = fmaf(weight_decay, pp[k], d);                      // d_p = g + wd * p
-      bb[k] = first_step ? d : fmaf(momentum, bb[k], d);     // buf = momentum * buf + d_p
-      pp[k] = fmaf(-lr, bb[k], pp[k]);                       // p -= lr * buf
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * stride;
+      if (i < n4) {
+        pv[u] = __ldcs(p4 + i); gv[u] = __ldcs(g4 + i);
+        bv[u] = first_step ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldcs(b4 + i);
+      }
     }
-    p4[i] = pv; b4[i] = bv;
-    if (zero_grad) g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * stride;
+      if (i < n4) {
+        float* pp = (float*)&pv[u]; float* gg = (float*)&gv[u]; float* bb = (float*)&bv[u];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float d = gg[k] * coef;
+          d = fmaf(weight_decay, pp[k], d);                      // d_p = g + wd * p
+          bb[k] = first_step ? d : fmaf(momentum, bb[k], d);     // buf = momentum * buf + d_p
+          pp[k] = fmaf(-lr, bb[k], pp[k]);                       // p -= lr * buf
+        }
+        __stcs(p4 + i, pv[u]); __stcs(b4 + i, bv[u]);
+        if (zero_grad) __stcs(g4 + i, make_float4(0.f, 0.f, 0.f, 0.f));
+      }
+    }
   }
   for (long long i = (n4 << 2) + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride) {
     float d = g[i] * coef;

@@ -57,17 +57,31 @@ class FlatSGD(object):
         self._works = []
         self._pending = {}
         self._distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
-        if self._distributed and overlap_comm:
-            # overlap the gradient all-reduce with backward: one hook per parameter counts down its
-            # chunk; the last one launches the chunk's all-reduce (NCCL stream) while autograd keeps going
-            for g in self.groups:
-                for ci, (a, b, ps) in enumerate(g.chunks):
-                    for p in ps:
-                        p.register_post_accumulate_grad_hook(self._make_hook(g, ci))
         self._overlap = self._distributed and overlap_comm
+        self._seen = set()
+        # One hook per parameter. (1) It marks the parameter's flat gradient as touched by autograd, which ends
+        # the window in which weight-gradient GEMMs may write straight into it (tc_ops.direct_grad_target).
+        # (2) With data-parallel overlap it counts down the parameter's communication chunk; the last one
+        # launches the chunk's all-reduce (NCCL stream) while autograd keeps going.
+        for g in self.groups:
+            for ci, (a, b, ps) in enumerate(g.chunks):
+                for p in ps:
+                    hook = self._make_hook(g, ci)
+                    p._mb200_direct = tc_ops.DirectGradState()
+                    p.register_post_accumulate_grad_hook(self._make_autograd_hook(hook))
+
+    def _make_autograd_hook(self, hook):
+        def on_accumulate(param):
+            param._mb200_direct.dirty = True
+            if self._overlap:
+                hook(param)
+        return on_accumulate
 
     def _make_hook(self, group, ci):
         def hook(param):
+            if id(param) in self._seen:      # count every parameter once per step
+                return
+            self._seen.add(id(param))
             key = (id(group), ci)
             left = self._pending.get(key, len(group.chunks[ci][2])) - 1
             self._pending[key] = left
@@ -82,6 +96,8 @@ class FlatSGD(object):
         if self.steps == 0:
             for g in self.groups:
                 g.flat_g.zero_()
+                for p in g.params:
+                    p._mb200_direct.reset()
 
     def all_reduce_grads(self):
         """Data-parallel average of the flat gradient buffers. With overlap the chunk all-reduces were
@@ -100,6 +116,7 @@ class FlatSGD(object):
                     if (id(g), a) not in done:
                         dist.all_reduce(g.flat_g[a:b], op=dist.ReduceOp.SUM)
             self._works, self._pending = [], {}
+            self._seen.clear()
             for g in self.groups:
                 g.flat_g.mul_(inv)
             return
@@ -120,5 +137,8 @@ class FlatSGD(object):
                                                  float(self.max_norm), first, 1, _c.cur_stream())
             _c.check(rc, "mb200_sgd_momentum_clip")
         self.steps += 1
+        for g in self.groups:                # gradients are zero again: re-open the direct-write window
+            for p in g.params:
+                p._mb200_direct.reset()
         tc_ops.bump_weight_epoch()       # raw-pointer update: invalidate the bf16 split caches
         return total

@@ -10,12 +10,14 @@ from torch.nn.modules.module import Module
 
 import motifs_cabi as _c
 from config import BATCHNORM_MOMENTUM
+from lib import mask_conv
 from lib.draw_rectangles.draw_rectangles import draw_union_boxes_cuda
 from lib.fpn.roi_align.functions.roi_align import RoIAlignFunction, roi_align_from_nhwc
 
 
 import os
 _MASKCONV_CHANNELS_LAST = os.environ.get("MOTIFS_MASKCONV_CL", "0") == "1"
+_MASKCONV_IMPL = os.environ.get("MOTIFS_MASKCONV", "own")   # "own": csrc/maskconv.cu + tcgen05 GEMM; "cudnn": torch modules
 _CUDNN_BENCHMARK = os.environ.get("MOTIFS_CUDNN_BENCHMARK", "1") == "1"   # let cuDNN pick its fastest fp32 algorithm
 
 
@@ -101,7 +103,12 @@ class UnionBoxesAndFeats(Module):
         if not self.use_feats:
             return union_pools.detach()
         rects = draw_union_boxes_cuda(pair_boxes, self.pooling_size * 4 - 1, offset=0.5)
-        # The mask conv net (7x7 s2 + 3x3) still runs on cuDNN this round; TF32 is
+        if _MASKCONV_IMPL == "own" and mask_conv.supported(self.conv):
+            # conv7x7/s2 + ReLU + BN + pool + conv3x3 + ReLU + BN (+ the residual add) on this library's kernels
+            if self.concat:
+                return torch.cat((union_pools, mask_conv.mask_conv_net(self.conv, rects)), 1)
+            return mask_conv.mask_conv_net(self.conv, rects, addend=union_pools)
+        # MOTIFS_MASKCONV=cudnn: the torch modules (cuDNN). The mask conv net (7x7 s2 + 3x3) on cuDNN; TF32 is
         # switched off so it stays inside the fp32 parity bar (TF32 alone costs ~1e-3 here).
         if _MASKCONV_CHANNELS_LAST:
             # NHWC kernels for the cuDNN conv / BN / pool of this branch (layout only; same arithmetic)

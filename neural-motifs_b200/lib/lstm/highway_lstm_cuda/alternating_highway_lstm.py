@@ -42,7 +42,7 @@ class _HighwayLayerFunction(Function):
     gate activations, which is what backward needs (elementWise_fp/bp, highway_lstm_kernel.cu:46-160)."""
 
     @staticmethod
-    def forward(ctx, P, Wh, bias, dropout, lengths_dev, direction, save_gates):
+    def forward(ctx, P, Wh, bias, dropout, lengths_dev, direction, save_gates, base=None):
         _c.require_cuda(P, Wh, bias, dropout, lengths_dev)
         P = P.contiguous()
         Wh = Wh.contiguous()
@@ -61,6 +61,7 @@ class _HighwayLayerFunction(Function):
         _c.check(rc, "mb200_highway_lstm_layer_forward")
         ctx.direction = direction
         ctx.have_gates = save_gates
+        ctx.base = base            # the flat parameter Wh is a view of (direct gradient writes, tc_ops.direct_grad_target)
         if save_gates:
             ctx.save_for_backward(P, Wh, h, c, dropout, lengths_dev)
         return h[1:]
@@ -93,12 +94,15 @@ class _HighwayLayerFunction(Function):
             else:
                 hp, g5 = h[2:].reshape((T - 1) * B, H), dG2[:(T - 1) * B, :5 * H]
             if hp.size(0) > 0:
-                dWh = tc_ops.gemm(tc_ops.split_transposed(hp), tc_ops.split_transposed(g5))
+                tgt = tc_ops.direct_grad_target(ctx.base, Wh) if ctx.base is not None else None
+                dWh = tc_ops.gemm(tc_ops.split_transposed(hp), tc_ops.split_transposed(g5), out=tgt)
+                if tgt is not None:
+                    dWh = None
             else:
                 dWh = torch.zeros_like(Wh)
         if ctx.needs_input_grad[2]:
             dbias = dG2[:, :5 * H].sum(0)
-        return dG, dWh, dbias, None, None, None, None
+        return dG, dWh, dbias, None, None, None, None, None
 
 
 class AlternatingHighwayLSTM(torch.nn.Module):
@@ -167,7 +171,8 @@ class AlternatingHighwayLSTM(torch.nn.Module):
             # hoisted input projection for every timestep at once (the reference does one small
             # cublasSgemm per step, highway_lstm_kernel.cu:441-452)
             P = tc_ops.matmul_tc(x.view(T * B, insz), wi, self.weight, ("wi", layer)).view(T, B, 6 * H)
-            x = _HighwayLayerFunction.apply(P, wh, b, dropout_weights[layer], lengths_dev, layer % 2, save_gates)
+            x = _HighwayLayerFunction.apply(P, wh, b, dropout_weights[layer], lengths_dev, layer % 2, save_gates,
+                                            self.weight)
         output = x
         output = pack_padded_sequence(output, lengths, batch_first=False)
         return output, None

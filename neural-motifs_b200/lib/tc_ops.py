@@ -77,13 +77,17 @@ def _prof_end(kind, flops, ev0):
     PROFILE.append((kind, float(flops), ev0, ev1))
 
 
-def gemm(A, B, bias=None, relu=False, want_f32=True, want_split=False):
+def gemm(A, B, bias=None, relu=False, want_f32=True, want_split=False, out=None):
     """C = A @ B^T (+bias)(relu) with A [M,K], B [N,K] SplitMats. Returns fp32 [M,N] and/or a SplitMat
-    of C (pitch round_up(N,64), zero padded) per the flags."""
+    of C (pitch round_up(N,64), zero padded) per the flags. `out`: contiguous fp32 [M,N] to write into."""
     assert A.Kp == B.Kp, (A.Kp, B.Kp)
     M, N = A.rows, B.rows
     dev = A.hi.device
-    C = torch.empty(M, N, dtype=torch.float32, device=dev) if want_f32 else None
+    if out is not None:
+        assert want_f32 and out.dtype == torch.float32 and out.is_contiguous() and out.numel() == M * N
+        C = out
+    else:
+        C = torch.empty(M, N, dtype=torch.float32, device=dev) if want_f32 else None
     Cs = None
     if want_split:
         Np = _round_up(N, 64)
@@ -154,6 +158,52 @@ def clear_cache():
     _cache.clear()
 
 
+# ------------------------------------------------------------------ direct gradient writes
+class DirectGradState(object):
+    """Attached (as `param._mb200_direct`) by lib/fused_optim.FlatSGD to parameters whose `.grad` is a view of a
+    flat buffer the fused step has just zeroed. A weight-gradient GEMM may then write its result straight into
+    `.grad` (or into the slice of it that belongs to a view of the parameter) instead of materialising a
+    temporary for autograd's AccumulateGrad to add: for fc6 that pass alone re-reads and re-writes 1.2 GB.
+    `written`: slices already written this step; `dirty`: AccumulateGrad has run since the last step (then
+    `.grad` is no longer known to be zero and the ordinary path is taken). The data-parallel chunk countdown
+    stays on the AccumulateGrad hook: torch runs it once per backward for every parameter in the graph, after
+    all of its uses have been differentiated, also when every use returned no gradient tensor — announcing a
+    parameter from the op that wrote it would be too early for a parameter used twice."""
+    __slots__ = ("written", "dirty")
+
+    def __init__(self):
+        self.written, self.dirty = set(), False
+
+    def reset(self):
+        self.written.clear()
+        self.dirty = False
+
+
+DIRECT_GRADS = True       # switch for A/B runs (bench.py --no-direct-grads)
+
+
+def direct_grad_target(param, view=None):
+    """The tensor a gradient GEMM may overwrite for `param` (or for `view`, a contiguous slice of it), else None."""
+    st = getattr(param, "_mb200_direct", None)
+    if not DIRECT_GRADS or st is None or st.dirty or param.grad is None or not param.grad.is_contiguous():
+        return None
+    if view is None:
+        if st.written:
+            return None
+        st.written.add("all")
+        return param.grad
+    if "all" in st.written or not view.is_contiguous():
+        return None
+    off = view.storage_offset() - param.storage_offset()
+    if off < 0 or off + view.numel() > param.numel():
+        return None
+    key = (off, view.numel())
+    if any(k[0] < off + view.numel() and off < k[0] + k[1] for k in st.written):
+        return None                                   # overlaps a slice already written this step
+    st.written.add(key)
+    return param.grad.view(-1)[off:off + view.numel()].view(view.shape)
+
+
 class _LinearTC(Function):
     @staticmethod
     def forward(ctx, x, weight, bias):
@@ -171,7 +221,10 @@ class _LinearTC(Function):
         if ctx.needs_input_grad[0]:
             gx = gemm(split_rows(gy), weight_split_t(weight))                 # [M,N] x [K,N]^T -> [M,K]
         if ctx.needs_input_grad[1]:
-            gw = gemm(split_transposed(gy), split_transposed(x.detach()))     # [N,M] x [K,M]^T -> [N,K]
+            tgt = direct_grad_target(weight)
+            gw = gemm(split_transposed(gy), split_transposed(x.detach()), out=tgt)     # [N,M] x [K,M]^T -> [N,K]
+            if tgt is not None:
+                gw = None
         if ctx.has_bias and ctx.needs_input_grad[2]:
             gb = gy.sum(0)
         return gx, gw, gb
@@ -196,7 +249,10 @@ class _MatmulTC(Function):
         if ctx.needs_input_grad[0]:
             gx = gemm(split_rows(gy), _cached_view(ctx.base, (ctx.tag, "R"), w, split_rows))   # gy @ w^T
         if ctx.needs_input_grad[1]:
-            gw = gemm(split_transposed(x.detach()), split_transposed(gy))                      # x^T @ gy
+            tgt = direct_grad_target(ctx.base, w)
+            gw = gemm(split_transposed(x.detach()), split_transposed(gy), out=tgt)             # x^T @ gy
+            if tgt is not None:
+                gw = None          # written into the slice of base.grad that belongs to this view
         return gx, gw, None, None
 
 

@@ -49,6 +49,15 @@ SIGNATURES = {
     "mb200_maxpool2_nhwc_split": (c_int, [P, P, c_int, c_int, c_int, c_int, P, P, P]),
     "mb200_maxpool3s2_forward": (c_int, [P, c_longlong, c_int, c_int, P, P, P]),
     "mb200_maxpool3s2_backward": (c_int, [P, P, c_longlong, c_int, c_int, P, P]),
+    "mb200_im2col7s2_split": (c_int, [P, c_int, c_int, c_int, c_longlong, P, P, P]),
+    "mb200_im2col3_nhwc_split": (c_int, [P, c_int, c_int, c_int, c_int, c_int, c_longlong, P, P, P]),
+    "mb200_bn_stats": (c_int, [P, c_longlong, c_int, c_float, c_float, P, P, P, P, P, P]),
+    "mb200_bn_pool3s2_nhwc": (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, P, P, P]),
+    "mb200_unpool3s2_nhwc": (c_int, [P, P, c_int, c_int, c_int, c_int, P, P]),
+    "mb200_bn_nhwc_to_nchw": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, P, P]),
+    "mb200_nchw_to_nhwc": (c_int, [P, c_int, c_int, c_int, P, P]),
+    "mb200_bn_relu_backward": (c_int, [P, P, P, P, P, c_longlong, c_int, P, P, P, P]),
+    "mb200_col2im3_nhwc": (c_int, [P, c_int, c_int, c_int, c_int, P, P]),
     "mb200_sgd_momentum_clip": (c_int, [P, P, P, c_longlong, c_float, c_float, c_float, P, c_float, c_int, c_int, P]),
     "mb200_sgemm": (c_int, [c_int, c_int, c_int, c_int, c_int, c_float, P, c_int, P, c_int, c_float, P, c_int, P]),
 }

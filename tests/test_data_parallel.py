@@ -85,3 +85,98 @@ def test_flat_sgd_overlapped_all_reduce_gloo_world2():
         avg = (out[10][i] + out[11][i]) / 2
         assert torch.allclose(out[0][i], avg, atol=1e-7) and torch.allclose(out[1][i], avg, atol=1e-7)
     assert float(out[0][6].abs().max()) == 0.0
+
+
+def _worker_flat_direct(rank, world, port, out):
+    """FlatSGD + direct gradient writes (tc_ops.direct_grad_target): weight gradients written straight into the
+    flat buffer by the producing op — whole parameters and slices of a flat parameter — while the remaining
+    gradients arrive through autograd. The stand-in ops below do on the CPU what _LinearTC / _MatmulTC /
+    _HighwayLayerFunction do with the GEMM's `out=`; the bookkeeping under test is the host logic."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "neural-motifs_b200"))
+    from lib.data_parallel import init_from_env
+    from lib.fused_optim import FlatSGD
+    from lib import tc_ops
+    init_from_env("gloo")
+
+    class DirectLinear(torch.autograd.Function):           # y = x @ w^T, w a whole parameter
+        @staticmethod
+        def forward(ctx, x, w):
+            ctx.save_for_backward(x, w)
+            return x @ w.t()
+
+        @staticmethod
+        def backward(ctx, gy):
+            x, w = ctx.saved_tensors
+            tgt = tc_ops.direct_grad_target(w)
+            gw = gy.t() @ x
+            if tgt is not None:
+                tgt.copy_(gw); gw = None
+            return gy @ w, gw
+
+    class DirectSlice(torch.autograd.Function):            # y = x @ v, v a contiguous slice of the flat `base`
+        @staticmethod
+        def forward(ctx, x, v, base):
+            ctx.save_for_backward(x, v); ctx.base = base
+            return x @ v
+
+        @staticmethod
+        def backward(ctx, gy):
+            x, v = ctx.saved_tensors
+            tgt = tc_ops.direct_grad_target(ctx.base, v)
+            gv = x.t() @ gy
+            if tgt is not None:
+                tgt.copy_(gv); gv = None
+            return gy @ v.t(), gv, None
+
+    def build():
+        torch.manual_seed(0)
+        return [torch.nn.Parameter(torch.randn(24, 16)), torch.nn.Parameter(torch.randn(16 * 8 + 8 * 8 + 8)),
+                torch.nn.Parameter(torch.randn(24, 24))]
+
+    def run(ps, x, direct):
+        w1, flat, w2 = ps
+        a, b, bias = flat[:128].view(16, 8), flat[128:192].view(8, 8), flat[192:]
+        lin = DirectLinear.apply if direct else (lambda t, w: t @ w.t())
+        sl = (lambda t, v: DirectSlice.apply(t, v, flat)) if direct else (lambda t, v: t @ v)
+        h = torch.tanh(lin(x, w1))                                          # [8,24]
+        h = lin(h, w2)                                                      # w2: its only use -> whole-param direct write
+        h2 = torch.tanh(sl(h[:, :16], a))                                   # slice 1 direct
+        h3 = sl(h2, b) + bias                                               # slice 2 direct, bias through autograd
+        y = lin(h3 @ torch.ones(8, 16), w1)                                 # w1 used twice: second use falls back to autograd
+        return y.pow(2).mean() + h.pow(2).mean()
+
+    ps = build()
+    opt = FlatSGD([(ps[:1], 0.1), (ps[1:], 0.01)], overlap_comm=True, chunk_bytes=1024)
+    opt.zero_grad()
+    torch.manual_seed(100 + rank)
+    x = torch.randn(8, 16)
+    run(ps, x, True).backward()
+    assert ps[2]._mb200_direct.written == {"all"}           # (torch still runs its AccumulateGrad hooks, with no gradient)
+    assert len(ps[1]._mb200_direct.written) == 2 and ps[1]._mb200_direct.dirty            # bias came through autograd
+    opt.all_reduce_grads()
+    out[rank] = [p.grad.clone() for p in ps]
+    ref = build()
+    run(ref, x, False).backward()
+    out[10 + rank] = [p.grad.clone() for p in ref]
+    # a second backward before any step must accumulate (the direct-write window is closed)
+    g_before = [p.grad.clone() for p in ps]
+    run(ps, x, True).backward()
+    opt._works, opt._pending = [], {}; opt._seen.clear()
+    out[20 + rank] = [(p.grad - g).clone() for p, g in zip(ps, g_before)]
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_flat_sgd_direct_gradient_writes_gloo_world2():
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker_flat_direct, args=(2, _free_port(), out), nprocs=2, join=True)
+    for i in range(3):
+        avg = (out[10][i] + out[11][i]) / 2
+        assert torch.allclose(out[0][i], avg, atol=1e-6), i
+        assert torch.allclose(out[1][i], avg, atol=1e-6), i
+        for r in (0, 1):        # second backward added this rank's own gradient on top (no overwrite)
+            assert torch.allclose(out[20 + r][i], out[10 + r][i], atol=1e-6), (r, i)

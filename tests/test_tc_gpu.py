@@ -136,3 +136,54 @@ def test_stem_conv_vs_fp64(cuda, B, H, W):
     ref = torch.nn.functional.conv2d(x.double(), conv.weight.double(), conv.bias.double(), padding=1).clamp_min(0)
     got = (yh.float() + yl.float()).permute(0, 3, 1, 2)
     assert relerr(got, ref) < 2e-5, relerr(got, ref)      # bounded by the bf16-pair output format (2^-17)
+
+
+def test_direct_gradient_writes_match_autograd_accumulation(cuda):
+    """FlatSGD parameters: weight-gradient GEMMs of linear_tc / the highway LSTM write straight into the flat
+    gradient buffer (tc_ops.direct_grad_target); the result must equal autograd's accumulate path bit for bit
+    (same GEMM, same inputs), over two optimizer steps."""
+    from torch.nn.utils.rnn import pack_padded_sequence
+    from lib import tc_ops
+    from lib.fused_optim import FlatSGD
+    from lib.lstm.highway_lstm_cuda.alternating_highway_lstm import AlternatingHighwayLSTM
+
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.fc1 = torch.nn.Linear(96, 128)
+            self.rnn = AlternatingHighwayLSTM(128, 64, num_layers=2, recurrent_dropout_probability=0.0)
+            self.fc2 = torch.nn.Linear(64, 10)
+
+        def forward(self, x, lengths):
+            T, B, _ = x.shape
+            h = tc_ops.linear_tc(x, self.fc1.weight, self.fc1.bias).relu()
+            out, _ = self.rnn(pack_padded_sequence(h, lengths))
+            y = tc_ops.linear_tc(out.data, self.fc2.weight, self.fc2.bias)
+            return y.pow(2).mean() + tc_ops.linear_tc(x.reshape(T * B, -1), self.fc1.weight, None).mean()   # fc1 used twice
+
+    def run(direct):
+        torch.manual_seed(3)
+        net = Net().to(cuda)
+        opt = FlatSGD([(list(net.parameters()), 0.05)], momentum=0.9, weight_decay=1e-4, max_norm=5.0)
+        tc_ops.DIRECT_GRADS = direct
+        grads = []
+        try:
+            for step in range(2):
+                torch.manual_seed(10 + step)
+                x = torch.randn(7, 4, 96, device=cuda)
+                opt.zero_grad()
+                net(x, torch.tensor([7, 6, 4, 2])).backward()
+                grads.append([p.grad.clone() for p in net.parameters()])
+                opt.step()
+        finally:
+            tc_ops.DIRECT_GRADS = True
+        return grads, [p.detach().clone() for p in net.parameters()], net
+
+    g_d, p_d, net = run(True)
+    g_a, p_a, _ = run(False)
+    assert any(len(p._mb200_direct.written) == 0 for p in net.parameters())      # states were reset by step()
+    for step in range(2):
+        for a, b, (n, _) in zip(g_d[step], g_a[step], net.named_parameters()):
+            assert torch.equal(a, b), (step, n, float((a - b).abs().max()))
+    for a, b in zip(p_d, p_a):
+        assert torch.equal(a, b)
