@@ -198,8 +198,19 @@ int mb200_nchw_to_nhwc(const float* x, int R, int C, int HW, float* out, cudaStr
  * (dgamma), dz = dL/dz [P,C], dbias[C] = column sums of dz (doubles; all three overwritten). */
 int mb200_bn_relu_backward(const float* g, const float* x, const float* mean, const float* invstd, const float* gamma,
                            long long P, int C, double* sums, float* dz, double* dbias, cudaStream_t stream);
+/* Fused form for the weight-gradient GEMMs: dz leaves as (hi, lo) bf16 pairs, transposed [C, Pp] (Pp % 64 == 0,
+ * zero padded; C % 32 == 0) and, when p_hi != NULL, plain [P, C]. argmax != NULL: g is the pooled gradient
+ * [R,Ho,Wo,C], routed through the 3x3/s2/p1 max-pool on the fly (P = R*H*W, x = the pool's input [R,H,W,C]). */
+int mb200_bn_relu_backward_split(const float* g, const unsigned char* argmax, const float* x, const float* mean,
+                                 const float* invstd, const float* gamma, long long P, long long Pp, int C, int H, int W,
+                                 double* sums, void* t_hi, void* t_lo, void* p_hi, void* p_lo, double* dbias,
+                                 cudaStream_t stream);
 /* dx[R,H,W,C] from dcol [R*H*W, 9C] (adjoint of mb200_im2col3_nhwc_split, transposed == 0). */
 int mb200_col2im3_nhwc(const float* dcol, int R, int H, int W, int C, float* dx, cudaStream_t stream);
+
+/* *acc += sum_i x[i]^2 (double accumulator on the device, caller zeroes it): the global gradient norm of
+ * clip_grad_norm (lib/pytorch_misc.py:416-459) as one pass per flat buffer. x 16-byte aligned. */
+int mb200_sumsq_accum(const float* x, long long n, double* acc, cudaStream_t stream);
 
 /* Fused clip + weight-decay + momentum SGD over a flat fp32 buffer (replaces the caller-side
  * clip_grad_norm + optim.SGD.step of models/train_rels.py:145-150). total_norm_dev: device scalar with

@@ -104,32 +104,38 @@ __global__ void im2col3_nhwc_kernel(const float* __restrict__ x, int R, int H, i
 __global__ void im2col3_nhwc_t_kernel(const float* __restrict__ x, int R, int H, int W, int C, long long P, long long Pp,
                                       __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
   __shared__ float tile[64][33];
-  __shared__ long long src[64];                                // element offset of the source pixel, -1 = zero padding
-  const int tap = blockIdx.z, c0 = blockIdx.y * 32;
+  __shared__ int pix[64];                                      // (r*H + h)*W + w of each pixel, -1 beyond P
+  __shared__ short ph[64], pw[64];
+  const int c0 = blockIdx.y * 32;
   const long long p0 = (long long)blockIdx.x * 64;
   const int tid = threadIdx.y * 32 + threadIdx.x;
   if (tid < 64) {
     const long long p = p0 + tid;
-    long long off = -1;
+    int q = -1, h = 0, w = 0;
     if (p < P) {
       const unsigned pu = (unsigned)p;                         // host guarantees P < 2^31
-      const int w = pu % W; const unsigned t = pu / W; const int h = t % H; const unsigned r = t / H;
-      const int yy = h + tap / 3 - 1, xx = w + tap % 3 - 1;
-      if (yy >= 0 && yy < H && xx >= 0 && xx < W) off = (((long long)r * H + yy) * W + xx) * C;
+      w = pu % W; h = (pu / W) % H; q = (int)pu;
     }
-    src[tid] = off;
+    pix[tid] = q; ph[tid] = (short)h; pw[tid] = (short)w;
   }
   __syncthreads();
+  for (int tap = 0; tap < 9; ++tap) {
+    const int dy = tap / 3 - 1, dx = tap % 3 - 1;
 #pragma unroll
-  for (int i = threadIdx.y; i < 64; i += 8) {
-    const long long off = src[i];
-    tile[i][threadIdx.x] = off >= 0 ? __ldg(x + off + c0 + threadIdx.x) : 0.f;
-  }
-  __syncthreads();
+    for (int i = threadIdx.y; i < 64; i += 8) {
+      const int q = pix[i], yy = ph[i] + dy, xx = pw[i] + dx;
+      float v = 0.f;
+      if (q >= 0 && yy >= 0 && yy < H && xx >= 0 && xx < W)
+        v = __ldg(x + ((long long)q + dy * W + dx) * C + c0 + threadIdx.x);
+      tile[i][threadIdx.x] = v;
+    }
+    __syncthreads();
 #pragma unroll
-  for (int i = threadIdx.y; i < 32; i += 8) {                  // i = channel within the block, threadIdx.x = pixel pair
-    const long long off = ((long long)tap * C + c0 + i) * Pp + p0 + 2 * threadIdx.x;
-    store_pair(hi, lo, off, tile[2 * threadIdx.x][i], tile[2 * threadIdx.x + 1][i]);
+    for (int i = threadIdx.y; i < 32; i += 8) {                // i = channel within the block, threadIdx.x = pixel pair
+      const long long off = ((long long)tap * C + c0 + i) * Pp + p0 + 2 * threadIdx.x;
+      store_pair(hi, lo, off, tile[2 * threadIdx.x][i], tile[2 * threadIdx.x + 1][i]);
+    }
+    __syncthreads();
   }
 }
 
@@ -331,6 +337,110 @@ __global__ void bn_relu_bwd_kernel(const float* __restrict__ g, const float* __r
   }
 }
 
+// ---------------------------------------------------------------- fused variants of the backward pair above
+// g is either a tensor [P,C] (UNPOOL == false) or gathered on the fly from the pooled gradient
+// gy [R,Ho,Wo,C] and the arg-max codes (UNPOOL == true: P = R*H*W rows, x is the pool's input).
+template <bool UNPOOL>
+__device__ __forceinline__ float grad_at(const float* __restrict__ g, const unsigned char* __restrict__ arg, long long p,
+                                         int c, int C, int H, int W, int Ho, int Wo) {
+  if (!UNPOOL) return __ldg(g + p * C + c);
+  const unsigned pu = (unsigned)p;
+  const int xx = pu % W, yy = (pu / W) % H;
+  const long long r = pu / ((unsigned)W * H);
+  float s = 0.f;
+  const int oy0 = yy / 2, oy1 = (yy + 1) / 2, ox0 = xx / 2, ox1 = (xx + 1) / 2;
+  for (int oy = oy0; oy <= oy1; ++oy) {
+    if (oy >= Ho) continue;
+    const int dy = yy - (2 * oy - 1);
+    for (int ox = ox0; ox <= ox1; ++ox) {
+      if (ox >= Wo) continue;
+      const long long o = ((r * Ho + oy) * Wo + ox) * C + c;
+      if (arg[o] == dy * 3 + (xx - (2 * ox - 1))) s += __ldg(g + o);
+    }
+  }
+  return s;
+}
+
+template <bool UNPOOL>
+__global__ void bn_bwd_reduce_kernel(const float* __restrict__ g, const unsigned char* __restrict__ arg,
+                                     const float* __restrict__ x, const float* __restrict__ mean,
+                                     const float* __restrict__ invstd, long long P, int C, int H, int W, int Ho, int Wo,
+                                     double* __restrict__ sums) {
+  __shared__ double red[2][8][32];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  float acc0 = 0.f, acc1 = 0.f;
+  if (c < C) {
+    const float mu = mean[c], is = invstd[c];
+    for (long long p = blockIdx.y * 8 + threadIdx.y; p < P; p += 8LL * gridDim.y) {
+      const float gv = grad_at<UNPOOL>(g, arg, p, c, C, H, W, Ho, Wo);
+      const float xh = (__ldg(x + p * C + c) - mu) * is;
+      acc0 += gv; acc1 = fmaf(gv, xh, acc1);
+    }
+  }
+  red[0][threadIdx.y][threadIdx.x] = (double)acc0;
+  red[1][threadIdx.y][threadIdx.x] = (double)acc1;
+  __syncthreads();
+  if (threadIdx.y < 2 && c < C) {
+    double t = 0.0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t += red[threadIdx.y][j][threadIdx.x];
+    atomicAdd(sums + (long long)threadIdx.y * C + c, t);
+  }
+}
+
+// dz as bf16 pairs: transposed [C, Pp] (always; columns P..Pp zeroed) and, when plain_hi != NULL, plain [P, C].
+// Grid (C/32, NB): a block owns 32 channels and walks 64-pixel tiles, so the bias gradient needs NB*C atomics.
+template <bool UNPOOL>
+__global__ void bn_relu_bwd_split_kernel(const float* __restrict__ g, const unsigned char* __restrict__ arg,
+                                         const float* __restrict__ x, const float* __restrict__ mean,
+                                         const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                         const double* __restrict__ sums, long long P, long long Pp, int C, int H, int W,
+                                         int Ho, int Wo, __nv_bfloat16* __restrict__ t_hi, __nv_bfloat16* __restrict__ t_lo,
+                                         __nv_bfloat16* __restrict__ p_hi, __nv_bfloat16* __restrict__ p_lo,
+                                         double* __restrict__ dbias) {
+  __shared__ float tile[64][33];
+  __shared__ double red[8][32];
+  const int c0 = blockIdx.x * 32, c = c0 + threadIdx.x;        // host guarantees C % 32 == 0
+  const float mu = mean[c], is = invstd[c];
+  const float k = gamma[c] * is;
+  const float mg = (float)(sums[c] / (double)P), mgx = (float)(sums[C + c] / (double)P);
+  float acc = 0.f;
+  for (long long p0 = (long long)blockIdx.y * 64; p0 < Pp; p0 += 64LL * gridDim.y) {
+#pragma unroll 2
+    for (int i = threadIdx.y; i < 64; i += 8) {
+      const long long p = p0 + i;
+      float d = 0.f;
+      if (p < P) {
+        const float xv = __ldg(x + p * C + c);
+        const float gv = grad_at<UNPOOL>(g, arg, p, c, C, H, W, Ho, Wo);
+        d = k * (gv - mg - (xv - mu) * is * mgx);
+        if (!(xv > 0.f)) d = 0.f;
+        if (p_hi) {
+          __nv_bfloat16 dh, dl; tc::split_bf16(d, dh, dl);
+          p_hi[p * C + c] = dh; p_lo[p * C + c] = dl;
+        }
+      }
+      tile[i][threadIdx.x] = d;
+      acc += d;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = threadIdx.y; i < 32; i += 8) {                // i = channel within the block, threadIdx.x = pixel pair
+      const long long off = ((long long)(c0 + i)) * Pp + p0 + 2 * threadIdx.x;
+      store_pair(t_hi, t_lo, off, tile[2 * threadIdx.x][i], tile[2 * threadIdx.x + 1][i]);
+    }
+    __syncthreads();
+  }
+  red[threadIdx.y][threadIdx.x] = (double)acc;
+  __syncthreads();
+  if (threadIdx.y == 0) {
+    double t = 0.0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t += red[j][threadIdx.x];
+    atomicAdd(dbias + c, t);
+  }
+}
+
 // ---------------------------------------------------------------- col2im of the 3x3/p1 im2col layout
 // dx[r,y,x,c] = sum_tap dcol[(r, y - dy, x - dx), tap*C + c]
 __global__ void col2im3_nhwc_kernel(const float* __restrict__ dcol, int R, int H, int W, int C, float* __restrict__ dx) {
@@ -392,7 +502,7 @@ int mb200_im2col3_nhwc_split(const float* x, int R, int H, int W, int C, int tra
   if (transposed) {
     if (C % 32 || Pp < P || Pp % 64) return MB200_ERR_ARG;
     if (Pp >= (1LL << 31)) return MB200_ERR_UNSUPPORTED;
-    dim3 grid((unsigned)(Pp / 64), C / 32, 9);
+    dim3 grid((unsigned)(Pp / 64), C / 32);
     im2col3_nhwc_t_kernel<<<grid, dim3(32, 8), 0, stream>>>(x, R, H, W, C, P, Pp, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo);
   } else {
     if (C % 4) return MB200_ERR_ARG;
@@ -471,6 +581,36 @@ int mb200_bn_relu_backward(const float* g, const float* x, const float* mean, co
   colsum2_kernel<1><<<grid, dim3(32, 8), 0, stream>>>(g, x, mean, invstd, P, C, sums);
   bn_relu_bwd_kernel<<<grid, dim3(32, 8), 0, stream>>>(g, x, mean, invstd, gamma, sums, P, C, dz, dbias);
   MB200_CHECK_LAUNCH("mb200_bn_relu_backward");
+  return MB200_OK;
+}
+
+// Fused form of mb200_bn_relu_backward for the weight-gradient GEMMs: dz leaves as bf16 (hi, lo) pairs, transposed
+// [C, Pp] (Pp % 64 == 0, zero padded) and optionally plain [P, C]; with argmax != NULL, g is the POOLED gradient
+// [R,Ho,Wo,C] and is routed through the 3x3/s2/p1 max-pool on the fly (P must be R*H*W).
+int mb200_bn_relu_backward_split(const float* g, const unsigned char* argmax, const float* x, const float* mean,
+                                 const float* invstd, const float* gamma, long long P, long long Pp, int C, int H, int W,
+                                 double* sums, void* t_hi, void* t_lo, void* p_hi, void* p_lo, double* dbias,
+                                 cudaStream_t stream) {
+  if (P <= 0 || C <= 0 || C % 32 || Pp < P || Pp % 64 || P >= (1LL << 31)) return MB200_ERR_ARG;
+  MB200_CHECK(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, stream));
+  MB200_CHECK(cudaMemsetAsync(dbias, 0, sizeof(double) * C, stream));
+  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  const dim3 rgrid = colsum_grid(P, C);
+  long long nb = (kNumSMs * 6) / (C / 32);
+  if (nb > Pp / 64) nb = Pp / 64;
+  if (nb < 1) nb = 1;
+  const dim3 agrid(C / 32, (unsigned)nb);
+  __nv_bfloat16 *th = (__nv_bfloat16*)t_hi, *tl = (__nv_bfloat16*)t_lo, *ph = (__nv_bfloat16*)p_hi, *pl = (__nv_bfloat16*)p_lo;
+  if (argmax) {
+    bn_bwd_reduce_kernel<true><<<rgrid, dim3(32, 8), 0, stream>>>(g, argmax, x, mean, invstd, P, C, H, W, Ho, Wo, sums);
+    bn_relu_bwd_split_kernel<true><<<agrid, dim3(32, 8), 0, stream>>>(g, argmax, x, mean, invstd, gamma, sums, P, Pp, C, H, W,
+                                                                       Ho, Wo, th, tl, ph, pl, dbias);
+  } else {
+    bn_bwd_reduce_kernel<false><<<rgrid, dim3(32, 8), 0, stream>>>(g, nullptr, x, mean, invstd, P, C, H, W, Ho, Wo, sums);
+    bn_relu_bwd_split_kernel<false><<<agrid, dim3(32, 8), 0, stream>>>(g, nullptr, x, mean, invstd, gamma, sums, P, Pp, C, H,
+                                                                        W, Ho, Wo, th, tl, ph, pl, dbias);
+  }
+  MB200_CHECK_LAUNCH("mb200_bn_relu_backward_split");
   return MB200_OK;
 }
 

@@ -58,7 +58,52 @@ __global__ void sgd_momentum_clip_kernel(float* __restrict__ p, float* __restric
   }
 }
 
+// sum of squares of a flat fp32 buffer, accumulated in double: fp32 per thread (a few hundred terms),
+// double across the block and across blocks (one atomic per block).
+__global__ void sumsq_kernel(const float* __restrict__ x, long long n, double* __restrict__ acc) {
+  const long long n4 = n >> 2;
+  const long long stride = (long long)blockDim.x * gridDim.x;
+  const float4* x4 = (const float4*)x;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  constexpr int U = 4;
+  for (long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x; i0 < n4; i0 += stride * U) {
+    float4 v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * stride;
+      v[u] = i < n4 ? __ldg(x4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      s0 = fmaf(v[u].x, v[u].x, s0); s1 = fmaf(v[u].y, v[u].y, s1);
+      s2 = fmaf(v[u].z, v[u].z, s2); s3 = fmaf(v[u].w, v[u].w, s3);
+    }
+  }
+  for (long long i = (n4 << 2) + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride) s0 = fmaf(x[i], x[i], s0);
+  double t = (double)s0 + (double)s1 + (double)s2 + (double)s3;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  __shared__ double red[8];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = t;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double b = 0.0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) b += red[j];
+    atomicAdd(acc, b);
+  }
+}
+
 }  // namespace
+
+extern "C" int mb200_sumsq_accum(const float* x, long long n, double* acc, cudaStream_t stream) {
+  if (n <= 0) return MB200_OK;
+  if (((uintptr_t)x) & 15) return MB200_ERR_ARG;
+  const int blocks = (int)min((long long)kNumSMs * 8, (n / 16 + 255) / 256 + 1);
+  sumsq_kernel<<<blocks, 256, 0, stream>>>(x, n, acc);
+  MB200_CHECK_LAUNCH("mb200_sumsq_accum");
+  return MB200_OK;
+}
 
 extern "C" int mb200_sgd_momentum_clip(float* params, float* grads, float* momentum_buf, long long n, float lr,
                                        float momentum, float weight_decay, const float* total_norm_dev,

@@ -126,9 +126,12 @@ class FlatSGD(object):
             g.flat_g.mul_(inv)
 
     def step(self):
-        norms = torch.stack([torch.linalg.vector_norm(g.flat_g) for g in self.groups])
-        total = torch.linalg.vector_norm(norms).reshape(1).contiguous()
         lib = _c.load()
+        acc = torch.zeros(1, dtype=torch.float64, device=self.groups[0].flat_g.device)
+        for g in self.groups:                # global gradient norm: one streaming pass per flat buffer
+            with torch.cuda.device(g.flat_g.device):
+                _c.check(lib.mb200_sumsq_accum(_c.ptr(g.flat_g), g.n, _c.ptr(acc), _c.cur_stream()), "mb200_sumsq_accum")
+        total = acc.sqrt().float()
         first = 1 if self.steps == 0 else 0
         for g in self.groups:
             with torch.cuda.device(g.flat_p.device):

@@ -9,6 +9,8 @@ Both convolutions are explicit-im2col x weight products on the tcgen05 bf16x3 GE
 BatchNorm statistics / apply, the pool, the layout changes and the whole backward are the NHWC streaming
 kernels of csrc/maskconv.cu. Nothing here falls back to cuDNN: `mask_conv_net` needs the CUDA library.
 """
+import os
+
 import torch
 from torch.autograd import Function
 
@@ -88,6 +90,30 @@ def _bn_relu_backward(g2d, x2d, mean, invstd, gamma):
     return dz, sums[C:].float(), sums[:C].float(), dbias.float()      # dz, dgamma, dbeta, dconv_bias
 
 
+# "1": BN/ReLU backward emits the GEMM operands (bf16 pairs, transposed / plain) directly and routes the pooled
+# gradient through the max-pool on the fly; "0": separate un-pool, fp32 dz, split kernels (kept for A/B runs).
+FUSED_BWD = os.environ.get("MOTIFS_MASKCONV_FUSED_BWD", "0") == "1"
+
+
+def _bn_relu_backward_split(g, arg, x2d, mean, invstd, gamma, H, W, want_plain):
+    """mb200_bn_relu_backward_split: returns (dz^T SplitMat [C, P], dz SplitMat [P, C] or None, dgamma, dbeta, dbias).
+    arg is None: g is [P,C]; else g is the pooled gradient [R,Ho,Wo,C] and arg its arg-max codes."""
+    P, C = x2d.shape
+    dev = x2d.device
+    Pp = _round_up(P, 64)
+    sums = torch.empty(2 * C, dtype=torch.float64, device=dev)
+    dbias = torch.empty(C, dtype=torch.float64, device=dev)
+    t_hi = torch.empty(C, Pp, dtype=torch.bfloat16, device=dev); t_lo = torch.empty_like(t_hi)
+    p_hi = p_lo = None
+    if want_plain:
+        p_hi = torch.empty(P, C, dtype=torch.bfloat16, device=dev); p_lo = torch.empty_like(p_hi)
+    _lib_call("mb200_bn_relu_backward_split", dev, _c.ptr(g), _c.ptr(arg), _c.ptr(x2d), _c.ptr(mean), _c.ptr(invstd),
+              _c.ptr(gamma), P, Pp, C, H, W, _c.ptr(sums), _c.ptr(t_hi), _c.ptr(t_lo), _c.ptr(p_hi), _c.ptr(p_lo),
+              _c.ptr(dbias))
+    plain = SplitMat(p_hi, p_lo, P, C, C) if want_plain else None
+    return SplitMat(t_hi, t_lo, C, P, Pp), plain, sums[C:].float(), sums[:C].float(), dbias.float()
+
+
 class _MaskConvNet(Function):
     """out[R,C2,7,7] = addend + BN2(ReLU(conv3x3(pool(BN1(ReLU(conv7x7s2(masks)))))))."""
 
@@ -137,23 +163,33 @@ class _MaskConvNet(Function):
         # BN2 / ReLU backward in NHWC
         g_nhwc = torch.empty(R * H2 * H2, C2, dtype=torch.float32, device=dev)
         _lib_call("mb200_nchw_to_nhwc", dev, _c.ptr(g), R, C2, H2 * H2, _c.ptr(g_nhwc))
-        dz2, dg2, dbe2, db2 = _bn_relu_backward(g_nhwc, y2, mean2, inv2, g2.detach())
+        if FUSED_BWD:
+            dz2_t, dz2_p, dg2, dbe2, db2 = _bn_relu_backward_split(g_nhwc, None, y2, mean2, inv2, g2.detach(), H2, H2, True)
+        else:
+            dz2, dg2, dbe2, db2 = _bn_relu_backward(g_nhwc, y2, mean2, inv2, g2.detach())
+            dz2_t, dz2_p = split_transposed(dz2), split_rows(dz2)
+            del dz2
         del g_nhwc
         # conv2: dW2 = dz2^T @ im2col(p1);  dp1 = col2im(dz2 @ W2mat)
-        dw2 = gemm(split_transposed(dz2), _im2col3(p1, True))                         # [C2, 9*C1]
+        dw2 = gemm(dz2_t, _im2col3(p1, True))                                         # [C2, 9*C1]
         dw2 = dw2.view(C2, 3, 3, C1).permute(0, 3, 1, 2).contiguous()
-        dcol = gemm(split_rows(dz2), _w3_t(w2))                                       # [P2, 9*C1]
-        del dz2
+        dcol = gemm(dz2_p, _w3_t(w2))                                                 # [P2, 9*C1]
+        del dz2_t, dz2_p
         dp1 = torch.empty(R, H2, H2, C1, dtype=torch.float32, device=dev)
         _lib_call("mb200_col2im3_nhwc", dev, _c.ptr(dcol), R, H2, H2, C1, _c.ptr(dp1))
         del dcol
         # pool / BN1 / ReLU backward
-        dbn1 = torch.empty(R * H1 * H1, C1, dtype=torch.float32, device=dev)
-        _lib_call("mb200_unpool3s2_nhwc", dev, _c.ptr(dp1), _c.ptr(arg1), R, H1, H1, C1, _c.ptr(dbn1))
-        dz1, dg1, dbe1, db1 = _bn_relu_backward(dbn1, y1, mean1, inv1, g1.detach())
-        del dbn1
+        if FUSED_BWD:
+            dz1_t, _, dg1, dbe1, db1 = _bn_relu_backward_split(dp1, arg1, y1, mean1, inv1, g1.detach(), H1, H1, False)
+        else:
+            dbn1 = torch.empty(R * H1 * H1, C1, dtype=torch.float32, device=dev)
+            _lib_call("mb200_unpool3s2_nhwc", dev, _c.ptr(dp1), _c.ptr(arg1), R, H1, H1, C1, _c.ptr(dbn1))
+            dz1, dg1, dbe1, db1 = _bn_relu_backward(dbn1, y1, mean1, inv1, g1.detach())
+            del dbn1
+            dz1_t = split_transposed(dz1)
+            del dz1
         # conv1: dW1 = dz1^T @ im2col(masks) (the masks themselves need no gradient)
-        dw1 = gemm(split_transposed(dz1), _im2col7s2(masks, True))                    # [C1, 128]
+        dw1 = gemm(dz1_t, _im2col7s2(masks, True))                                    # [C1, 128]
         dw1 = dw1[:, :98].reshape(C1, 7, 7, 2).permute(0, 3, 1, 2).contiguous()
         return (None, g if ctx.has_addend else None, dw1, db1, dg1, dbe1, dw2, db2, dg2, dbe2, None, None, None)
 
@@ -170,7 +206,8 @@ def supported(conv_seq):
     ok = ok and isinstance(r1, nn.ReLU) and isinstance(n1, nn.BatchNorm2d) and n1.affine and n1.track_running_stats
     ok = ok and isinstance(pl, nn.MaxPool2d) and pl.kernel_size == 3 and pl.stride == 2 and pl.padding == 1
     ok = ok and isinstance(c2, nn.Conv2d) and c2.kernel_size == (3, 3) and c2.stride == (1, 1) and c2.padding == (1, 1) \
-        and c2.bias is not None and c2.in_channels % 32 == 0 and c2.in_channels == c1.out_channels
+        and c2.bias is not None and c2.in_channels % 32 == 0 and c2.in_channels == c1.out_channels \
+        and c2.out_channels % 64 == 0
     ok = ok and isinstance(r2, nn.ReLU) and isinstance(n2, nn.BatchNorm2d) and n2.affine and n2.track_running_stats
     return bool(ok and n1.momentum is not None and n2.momentum is not None)
 

@@ -163,8 +163,8 @@ def _worker_flat_direct(rank, world, port, out):
     out[10 + rank] = [p.grad.clone() for p in ref]
     # a second backward before any step must accumulate (the direct-write window is closed)
     g_before = [p.grad.clone() for p in ps]
+    opt._overlap = False                                  # no asynchronous all-reduce while the deltas are read
     run(ps, x, True).backward()
-    opt._works, opt._pending = [], {}; opt._seen.clear()
     out[20 + rank] = [(p.grad - g).clone() for p, g in zip(ps, g_before)]
     dist.barrier()
     dist.destroy_process_group()

@@ -141,6 +141,38 @@ def test_bn_relu_backward(cuda):
     assert relerr(dbias, z.grad.sum(0)) < 1e-4
 
 
+@pytest.mark.parametrize("unpool", [False, True])
+def test_bn_relu_backward_split_matches_unfused(cuda, unpool):
+    """The fused backward (bf16-pair outputs, optional on-the-fly un-pool) against the separate kernels."""
+    from lib import mask_conv
+    import motifs_cabi as c
+    torch.manual_seed(6)
+    R, H, C = 5, 14, 256
+    x = torch.randn(R, H, H, C, device=cuda).clamp_min(0)
+    x2d = x.view(-1, C)
+    P = x2d.size(0)
+    gamma = torch.randn(C, device=cuda)
+    mean, invstd = mask_conv._bn_stats(x2d, 1e-5, 0.0, None, None)
+    if unpool:
+        Ho = 7
+        gy = torch.randn(R, Ho, Ho, C, device=cuda)
+        arg = torch.randint(0, 9, (R, Ho, Ho, C), device=cuda, dtype=torch.uint8)
+        arg[:, 0] = arg[:, 0].clamp_min(3); arg[:, :, 0] = (arg[:, :, 0] // 3) * 3 + (arg[:, :, 0] % 3).clamp_min(1)  # stay inside the map
+        g_full = torch.empty(R, H, H, C, device=cuda)
+        c.check(c.load().mb200_unpool3s2_nhwc(c.ptr(gy), c.ptr(arg), R, H, H, C, c.ptr(g_full), c.cur_stream()), "unpool")
+        g_in, a_in, g2d = gy, arg, g_full.view(-1, C)
+    else:
+        g2d = torch.randn(P, C, device=cuda)
+        g_in, a_in = g2d, None
+    dz, dgamma, dbeta, dbias = mask_conv._bn_relu_backward(g2d, x2d, mean, invstd, gamma)
+    t, pl, dgamma2, dbeta2, dbias2 = mask_conv._bn_relu_backward_split(g_in, a_in, x2d, mean, invstd, gamma, H, H, True)
+    assert relerr(recon(pl), dz) < 2e-5
+    rt = recon(t)
+    assert rt.shape == (C, (P + 63) // 64 * 64)
+    assert relerr(rt[:, :P], dz.t()) < 2e-5 and float(rt[:, P:].abs().max()) == 0.0
+    assert relerr(dgamma2, dgamma) < 1e-6 and relerr(dbeta2, dbeta) < 1e-6 and relerr(dbias2, dbias) < 1e-5
+
+
 def _make_net(dev, dim=512):
     from torch import nn
     torch.manual_seed(11)
@@ -177,10 +209,11 @@ def _ref_with_decisions(ref_net, masks, saved, addend):
     return F.batch_norm(x2, None, None, n2.weight, n2.bias, True, 0.0, n2.eps) + addend.detach().double()
 
 
-@pytest.mark.parametrize("R", [37, 128])
-def test_mask_conv_net_forward_backward(cuda, R):
+@pytest.mark.parametrize("R,fused", [(37, True), (128, True), (37, False)])
+def test_mask_conv_net_forward_backward(cuda, R, fused, monkeypatch):
     import copy
     from lib import mask_conv
+    monkeypatch.setattr(mask_conv, "FUSED_BWD", fused)
     net = _make_net(cuda)
     ref_net = copy.deepcopy(net).double()
     ref_net2 = copy.deepcopy(net).double()
