@@ -11,12 +11,14 @@ from config import RELS_PER_IMG, REL_FG_FRACTION
 from lib.pytorch_misc import random_choose
 
 
-def proposal_assignments_gtbox(rois, gt_boxes, gt_classes, gt_rels, image_offset, fg_thresh=0.5, rng=np.random):
+def proposal_assignments_gtbox(rois, gt_boxes, gt_classes, gt_rels, image_offset, fg_thresh=0.5, rng=np.random,
+                               num_im=None):
     """rois [N,5]; gt_classes [N,2] (global image idx, class); gt_rels [R,4] (global image idx,
     subj, obj, predicate) with box indices local to the image. Returns (rois, labels [N],
     rel_labels [n,4] = (local image idx, subj row, obj row, predicate))."""
     im_inds = rois[:, 0].long()
-    num_im = int(im_inds[-1]) + 1
+    if num_im is None:                       # callers that hold the host copy of the image indices pass it in
+        num_im = int(im_inds[-1]) + 1
     n = im_inds.size(0)
     fg_rels = gt_rels.clone()
     fg_rels[:, 0] -= image_offset

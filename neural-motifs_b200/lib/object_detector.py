@@ -170,14 +170,15 @@ class ObjectDetector(nn.Module):
         return rois, None, None, None, None, None
 
     def gt_boxes(self, fmap, im_sizes, image_offset, gt_boxes=None, gt_classes=None, gt_rels=None,
-                 train_anchor_inds=None, proposals=None):
+                 train_anchor_inds=None, proposals=None, im_inds_host=None):
         assert gt_boxes is not None
         im_inds = gt_classes[:, 0] - image_offset
         rois = torch.cat((im_inds.float()[:, None], gt_boxes), 1)
         if gt_rels is not None and self.training:
             rois, labels, rel_labels = proposal_assignments_gtbox(
                 rois.detach(), gt_boxes.detach(), gt_classes.detach(), gt_rels.detach(), image_offset, fg_thresh=0.5,
-                rng=getattr(self, "rng", np.random))
+                rng=getattr(self, "rng", np.random),
+                num_im=(int(im_inds_host[-1]) + 1) if im_inds_host is not None and len(im_inds_host) else None)
         else:
             labels = gt_classes[:, 1]
             rel_labels = None
@@ -208,17 +209,26 @@ class ObjectDetector(nn.Module):
         return fn(*args, **kwargs)
 
     def forward(self, x, im_sizes, image_offset, gt_boxes=None, gt_classes=None, gt_rels=None, proposals=None,
-                train_anchor_inds=None, return_fmap=False):
+                train_anchor_inds=None, return_fmap=False, im_inds_host=None):
+        """`im_inds_host` (superset of the reference signature): host copy of the GT image indices the caller has
+        already read back; with it the GT-box assignment — whose `nonzero` needs the host anyway — runs BEFORE the
+        backbone is queued, so the host never waits on the backbone."""
         frozen = not any(p.requires_grad for p in self.parameters())
         with torch.set_grad_enabled(torch.is_grad_enabled() and not frozen):
             return self._forward(x, im_sizes, image_offset, gt_boxes, gt_classes, gt_rels, proposals,
-                                 train_anchor_inds, return_fmap)
+                                 train_anchor_inds, return_fmap, im_inds_host)
 
     def _forward(self, x, im_sizes, image_offset, gt_boxes, gt_classes, gt_rels, proposals, train_anchor_inds,
-                 return_fmap):
+                 return_fmap, im_inds_host=None):
+        boxes_first = self.mode == 'gtbox' and im_inds_host is not None
+        if boxes_first:         # depends on the inputs only (gt_boxes() never touches the feature map)
+            got = self.gt_boxes(None, im_sizes, image_offset, gt_boxes, gt_classes, gt_rels, train_anchor_inds,
+                                proposals=proposals, im_inds_host=im_inds_host)
         fmap = self.feature_map(x)
-        rois, obj_labels, bbox_targets, rpn_scores, rpn_box_deltas, rel_labels = self.get_boxes(
-            fmap, im_sizes, image_offset, gt_boxes, gt_classes, gt_rels, train_anchor_inds, proposals=proposals)
+        if not boxes_first:
+            got = self.get_boxes(fmap, im_sizes, image_offset, gt_boxes, gt_classes, gt_rels, train_anchor_inds,
+                                 proposals=proposals)
+        rois, obj_labels, bbox_targets, rpn_scores, rpn_box_deltas, rel_labels = got
         obj_fmap = self.obj_feature_map(fmap, rois)
         od_obj_dists = tc_ops.linear_tc(obj_fmap, self.score_fc.weight, self.score_fc.bias)
         od_box_deltas = tc_ops.linear_tc(obj_fmap, self.bbox_fc.weight, self.bbox_fc.bias).view(

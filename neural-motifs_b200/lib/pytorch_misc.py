@@ -39,11 +39,12 @@ def gather_nd(x, index):
     return x.reshape(-1, dim)[sel]
 
 
-def image_segments(im_inds):
+def image_segments(im_inds, host=None):
     """Runs of equal image index as a python list [(image, start, end)]. One small D2H read of the
-    [N] index vector (the reference does the same, pytorch_misc.py:279); callers that already
-    know the per-image counts should pass them around instead of calling this again."""
-    a = im_inds.detach().cpu().numpy()
+    [N] index vector (the reference does the same, pytorch_misc.py:279) unless the caller already holds
+    its host copy (`host`, numpy): a D2H in the middle of forward drains the stream and the GPU then
+    idles while the host queues the next kernels."""
+    a = np.asarray(host) if host is not None else im_inds.detach().cpu().numpy()
     if a.shape[0] == 0:
         return []
     cuts = np.flatnonzero(a[1:] != a[:-1]) + 1

@@ -11,6 +11,8 @@ Every GEMM goes through the tcgen05 path (lib/tc_ops.py), the LSTMs through the 
 (csrc/lstm.cu), RoIAlign / union boxes / masks through csrc/roi_align.cu and csrc/boxes.cu."""
 import math
 
+import os
+
 import numpy as np
 import torch
 import torch.nn as nn
@@ -33,13 +35,18 @@ from lib.word_vectors import obj_edge_vectors
 
 MODES = ('sgdet', 'sgcls', 'predcls')
 
+# With GT boxes (sgcls / predcls) the image index of every object is an INPUT (gt_classes[:, 0]): read it back once,
+# before the backbone is queued, and hand the host copy to the code that builds the packed-sequence order, instead of
+# three D2H reads in the middle of forward (each one drains the stream). "0" keeps the reference's read-back points.
+EARLY_HOST_INDS = os.environ.get("MOTIFS_EARLY_HOST_INDS", "0") == "1"
 
-def _sort_by_score(im_inds, scores):
+
+def _sort_by_score(im_inds, scores, host=None):
     """Permutation that keeps each image's objects together, longest image first, ordered by
     descending score inside an image; its inverse; per-timestep batch sizes (rel_model.py:31-61).
     The fp32 key `score - 2*(2*(s-e)*num_im + i)` is the reference's, bit for bit."""
-    segs = image_segments(im_inds)
-    num_im = int(im_inds[-1]) + 1
+    segs = image_segments(im_inds, host)
+    num_im = (int(host[-1]) if host is not None else int(im_inds[-1])) + 1
     rois_per_image = np.zeros(num_im, dtype=np.float32)
     lengths = []
     for i, s, e in segs:
@@ -125,7 +132,7 @@ class LinearizedContext(nn.Module):
             return None
         return self.dropout_masks.get(name)
 
-    def sort_rois(self, batch_idx, confidence, box_priors):
+    def sort_rois(self, batch_idx, confidence, box_priors, host=None):
         """rel_model.py:139-161."""
         cxcywh = center_size(box_priors)
         if self.order == 'size':
@@ -140,23 +147,24 @@ class LinearizedContext(nn.Module):
             scores = centers / (centers.max() + 1)
         else:
             raise ValueError("invalid mode {}".format(self.order))
-        return _sort_by_score(batch_idx, scores)
+        return _sort_by_score(batch_idx, scores, host)
 
-    def edge_ctx(self, obj_feats, obj_dists, im_inds, obj_preds, box_priors=None):
+    def edge_ctx(self, obj_feats, obj_dists, im_inds, obj_preds, box_priors=None, im_inds_host=None):
         """rel_model.py:171-195."""
         obj_embed2 = self.obj_embed2(obj_preds)
         inp_feats = torch.cat((obj_embed2, obj_feats), 1)
         confidence = F.softmax(obj_dists, dim=1).detach().view(-1)[
             obj_preds.detach() + arange(obj_preds) * self.num_classes]
-        perm, inv_perm, ls_transposed = self.sort_rois(im_inds.detach(), confidence, box_priors)
+        perm, inv_perm, ls_transposed = self.sort_rois(im_inds.detach(), confidence, box_priors, im_inds_host)
         edge_input_packed = PackedSequence(inp_feats[perm], torch.as_tensor(ls_transposed))
         edge_reps = self.edge_ctx_rnn(edge_input_packed, dropout_weights=self._mask("edge_ctx_rnn"))[0][0]
         return edge_reps[inv_perm]
 
-    def obj_ctx(self, obj_feats, obj_dists, im_inds, obj_labels=None, box_priors=None, boxes_per_cls=None):
+    def obj_ctx(self, obj_feats, obj_dists, im_inds, obj_labels=None, box_priors=None, boxes_per_cls=None,
+                im_inds_host=None):
         """rel_model.py:197-234."""
         confidence = F.softmax(obj_dists, dim=1).detach()[:, 1:].max(1)[0]
-        perm, inv_perm, ls_transposed = self.sort_rois(im_inds.detach(), confidence, box_priors)
+        perm, inv_perm, ls_transposed = self.sort_rois(im_inds.detach(), confidence, box_priors, im_inds_host)
         obj_inp_rep = obj_feats[perm].contiguous()
         bs = torch.as_tensor(ls_transposed)
         encoder_rep = self.obj_ctx_rnn(PackedSequence(obj_inp_rep, bs), dropout_weights=self._mask("obj_ctx_rnn"))[0][0]
@@ -176,8 +184,9 @@ class LinearizedContext(nn.Module):
         encoder_rep = encoder_rep[inv_perm]
         return obj_dists, obj_preds, encoder_rep
 
-    def forward(self, obj_fmaps, obj_logits, im_inds, obj_labels=None, box_priors=None, boxes_per_cls=None):
-        """rel_model.py:236-296."""
+    def forward(self, obj_fmaps, obj_logits, im_inds, obj_labels=None, box_priors=None, boxes_per_cls=None,
+                im_inds_host=None):
+        """rel_model.py:236-296. `im_inds_host`: optional numpy copy of im_inds the caller already holds."""
         obj_embed = tc_ops.matmul_tc(F.softmax(obj_logits, dim=1), self.obj_embed.weight, self.obj_embed.weight, "E")
         pe = self.pos_embed
         pos = pe[0](center_size(box_priors))
@@ -188,7 +197,7 @@ class LinearizedContext(nn.Module):
 
         if self.nl_obj > 0:
             obj_dists2, obj_preds, obj_ctx = self.obj_ctx(obj_pre_rep, obj_logits, im_inds, obj_labels, box_priors,
-                                                          boxes_per_cls)
+                                                          boxes_per_cls, im_inds_host)
         else:
             if self.mode == 'predcls':
                 obj_dists2 = to_onehot(obj_labels.detach(), self.num_classes)
@@ -212,7 +221,7 @@ class LinearizedContext(nn.Module):
         if self.nl_edge > 0:
             edge_ctx = self.edge_ctx(torch.cat((obj_fmaps, obj_ctx), 1) if self.pass_in_obj_feats_to_edge else obj_ctx,
                                      obj_dists=obj_dists2.detach(), im_inds=im_inds, obj_preds=obj_preds,
-                                     box_priors=box_priors)
+                                     box_priors=box_priors, im_inds_host=im_inds_host)
         return obj_dists2, obj_preds, edge_ctx
 
 
@@ -316,8 +325,11 @@ class RelModel(nn.Module):
 
     def forward(self, x, im_sizes, image_offset, gt_boxes=None, gt_classes=None, gt_rels=None, proposals=None,
                 train_anchor_inds=None, return_fmap=False):
+        im_inds_host = None
+        if EARLY_HOST_INDS and self.detector.mode == 'gtbox' and gt_classes is not None:
+            im_inds_host = (gt_classes[:, 0] - image_offset).cpu().numpy()      # the one early read-back
         result = self.detector(x, im_sizes, image_offset, gt_boxes, gt_classes, gt_rels, proposals,
-                               train_anchor_inds, return_fmap=True)
+                               train_anchor_inds, return_fmap=True, im_inds_host=im_inds_host)
         if result.is_none():
             return ValueError("heck")   # rel_model.py:474-475 returns (does not raise) this
 
@@ -337,7 +349,7 @@ class RelModel(nn.Module):
         result.rm_obj_dists, result.obj_preds, edge_ctx = self.context(
             result.obj_fmap, result.rm_obj_dists.detach(), im_inds,
             result.rm_obj_labels if self.training or self.mode == 'predcls' else None,
-            boxes.detach(), result.boxes_all)
+            boxes.detach(), result.boxes_all, im_inds_host=im_inds_host)
 
         if edge_ctx is None:
             edge_rep = self.post_emb(result.obj_preds)

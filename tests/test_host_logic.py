@@ -48,6 +48,9 @@ def test_sort_by_score_matches_oracle():
     # images come out longest first, each image's objects by descending score
     first = im[p.numpy()][:ls[0]]
     assert len(set(first.tolist())) == ls[0]
+    # the caller-held host copy of the image indices (MOTIFS_EARLY_HOST_INDS) gives the same permutation
+    p2, ip2, ls2 = _sort_by_score(torch.from_numpy(im), scores, host=im)
+    assert torch.equal(p2, p) and torch.equal(ip2, ip) and list(ls2) == list(ls)
 
 
 def test_proposal_assignments_gtbox_matches_oracle():
@@ -60,6 +63,8 @@ def test_proposal_assignments_gtbox_matches_oracle():
     _, labels, rel = proposal_assignments_gtbox(rois, gt_boxes, gt_classes, gt_rels, 6, rng=np.random.RandomState(3))
     exp = OM.proposal_assignments_gtbox(rois, gt_boxes, gt_classes, gt_rels, 6, np.random.RandomState(3))
     assert torch.equal(rel, exp) and rel.shape == (768, 4)
+    _, _, rel2 = proposal_assignments_gtbox(rois, gt_boxes, gt_classes, gt_rels, 6, rng=np.random.RandomState(3), num_im=3)
+    assert torch.equal(rel2, exp)
     assert torch.equal(labels, gt_classes[:, 1])
     assert int((rel[:, 3] > 0).sum()) == 45          # every GT relation kept (45 <= 0.25 * 256 * 3)
 
