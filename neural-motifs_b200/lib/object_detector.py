@@ -9,6 +9,8 @@ What runs where (B200 path): VGG16 conv1_1..conv5_3 on the tcgen05 implicit-GEMM
 kernel; fc6/fc7/score_fc/bbox_fc and the RPN 1x1 conv on the tcgen05 GEMM; box decode fused
 (csrc/boxes.cu); RPN proposal NMS and the per-class detection NMS each as ONE segmented
 on-device launch pair (csrc/nms.cu) instead of <=150 host round trips per image (:445-452)."""
+import os
+
 import numpy as np
 import torch
 import torch.nn as nn
@@ -72,6 +74,19 @@ def load_vgg(use_dropout=True, use_relu=True, use_linear=True, pretrained=False)
     return model
 
 
+def load_resnet(pretrained=False):
+    """torchvision resnet101 minus layer4 / avgpool / fc (object_detector.py:615-620); weights come from the state
+    dict (no network here)."""
+    if pretrained:
+        raise ValueError("pretrained ImageNet weights are not available offline; load a state dict instead")
+    from torchvision.models.resnet import resnet101
+    model = resnet101(weights=None)
+    del model.layer4
+    del model.avgpool
+    del model.fc
+    return model
+
+
 def run_classifier(classifier, x, dropout_masks=None, prefix=""):
     """Apply a (possibly trimmed) VGG classifier Sequential — Linear / ReLU / Dropout — with the
     Linear layers on the tcgen05 GEMM. `dropout_masks` ({name: mask}) injects masks for parity runs."""
@@ -99,8 +114,10 @@ class ObjectDetector(nn.Module):
         super().__init__()
         if mode not in self.MODES:
             raise ValueError("invalid mode")
-        if use_resnet:
-            raise NotImplementedError("ResNet-101 backbone (BASELINE config 3) is not built yet; the reference's "
+        if use_resnet and os.environ.get("MOTIFS_EXPERIMENTAL_RESNET", "0") != "1":
+            raise NotImplementedError("ResNet-101 backbone (BASELINE config 3): the layer walk (lib/resnet_tc.py) is "
+                                      "pinned on the CPU but has not run on a B200 yet — set "
+                                      "MOTIFS_EXPERIMENTAL_RESNET=1 to use it. The reference's "
                                       "RelModel(use_resnet=True) is itself broken (SURVEY.md §8a a1')")
         self.mode = mode
         self.classes = classes
@@ -110,12 +127,21 @@ class ObjectDetector(nn.Module):
         self.max_per_img = max_per_img
         self.use_resnet = use_resnet
         self.thresh = thresh
-        vgg_model = load_vgg()
-        self.features = vgg_model.features
-        self.roi_fmap = vgg_model.classifier
-        self.score_fc = nn.Linear(4096, self.num_classes)
-        self.bbox_fc = nn.Linear(4096, self.num_classes * 4)
-        self.rpn_head = RPNHead(dim=512, input_dim=512)
+        if not use_resnet:
+            vgg_model = load_vgg()
+            self.features = vgg_model.features
+            self.roi_fmap = vgg_model.classifier
+            rpn_input_dim, output_dim = 512, 4096
+        else:                           # object_detector.py:84-101 (same module tree -> same state-dict keys)
+            self.features = load_resnet()
+            self.compress = nn.Sequential(nn.Conv2d(1024, 256, kernel_size=1), nn.ReLU(inplace=True),
+                                          nn.BatchNorm2d(256))
+            self.roi_fmap = nn.Sequential(nn.Linear(256 * 7 * 7, 2048), nn.SELU(inplace=True), nn.AlphaDropout(p=0.05),
+                                          nn.Linear(2048, 2048), nn.SELU(inplace=True), nn.AlphaDropout(p=0.05))
+            rpn_input_dim, output_dim = 1024, 2048
+        self.score_fc = nn.Linear(output_dim, self.num_classes)
+        self.bbox_fc = nn.Linear(output_dim, self.num_classes * 4)
+        self.rpn_head = RPNHead(dim=512, input_dim=rpn_input_dim)
         self.dropout_masks = None     # {"roi_fmap.2": mask, "roi_fmap.5": mask} for parity runs
         self._fmap_nhwc = None
         self._fmap_split = None
@@ -135,12 +161,33 @@ class ObjectDetector(nn.Module):
                                       "tcgen05 convolution is forward only (SURVEY.md §8f f1)")
         with torch.no_grad():
             need_split = self.mode in ('rpntrain', 'refinerels')
-            nhwc, split = tc_ops.vgg_features_forward(x, self._convs(), want_last_split=need_split)
+            if self.use_resnet:         # conv1 .. layer3 (:119-127) walked on the kernels, NHWC [B,37,37,1024]
+                from lib.resnet_tc import resnet_c4_forward, KernelOps
+                nhwc = resnet_c4_forward(self.features, x.contiguous().float(), KernelOps()).contiguous()
+                split = None
+                if need_split:
+                    B, H, W, C = nhwc.shape
+                    sp = tc_ops.split_rows(nhwc.view(-1, C))
+                    split = (sp.hi.view(B, H, W, C), sp.lo.view(B, H, W, C))
+            else:
+                nhwc, split = tc_ops.vgg_features_forward(x, self._convs(), want_last_split=need_split)
         self._fmap_nhwc, self._fmap_split = nhwc, split
         return nhwc.permute(0, 3, 1, 2)
 
     def obj_feature_map(self, features, rois):
         """RoIAlign 7x7 + fc6/fc7 (object_detector.py:129-138)."""
+        if self.use_resnet:             # :136-137: RoIAlign over compress(features) = 1x1 conv 1024->256 + ReLU + BN
+            c, bn = self.compress[0], self.compress[2]
+            B, C, H, W = features.shape
+            rows = features.permute(0, 2, 3, 1).reshape(-1, C)
+            y = torch.relu(tc_ops.linear_tc(rows, c.weight.view(c.out_channels, -1), c.bias))
+            y = F.batch_norm(y, bn.running_mean, bn.running_var, bn.weight, bn.bias, bn.training, bn.momentum, bn.eps)
+            if not y.requires_grad:
+                pool = roi_align_from_nhwc(y.view(B, H, W, -1), rois, self.pooling_size, self.pooling_size, 1 / 16)
+            else:
+                pool = RoIAlignFunction(self.pooling_size, self.pooling_size, spatial_scale=1 / 16)(
+                    y.view(B, H, W, -1).permute(0, 3, 1, 2), rois)
+            return run_classifier(self.roi_fmap, pool.reshape(rois.size(0), -1), self.dropout_masks, "roi_fmap.")
         if self._fmap_nhwc is not None and features.data_ptr() == self._fmap_nhwc.data_ptr() and not features.requires_grad:
             pool = roi_align_from_nhwc(self._fmap_nhwc, rois, self.pooling_size, self.pooling_size, 1 / 16)
         else:

@@ -297,9 +297,9 @@ def _conv_weight_split(conv_weight):
     return _cached(conv_weight, "conv", mk)
 
 
-def conv3x3_relu(xs, B, H, W, Cin, conv, want_f32=False, want_split=True):
-    """xs: (hi, lo) NHWC bf16 tensors [B,H,W,Cin]; conv: nn.Conv2d(3x3, pad 1). ReLU fused.
-    Returns (y_f32 NHWC or None, (yhi, ylo) or None)."""
+def conv3x3_relu(xs, B, H, W, Cin, conv, want_f32=False, want_split=True, relu=True):
+    """xs: (hi, lo) NHWC bf16 tensors [B,H,W,Cin]; conv: nn.Conv2d(3x3, pad 1, stride 1). Bias (if the
+    module has one) and ReLU (`relu`) fused. Returns (y_f32 NHWC or None, (yhi, ylo) or None)."""
     wsp = _conv_weight_split(conv.weight)
     Cout = conv.weight.size(0)
     dev = xs[0].device
@@ -309,7 +309,8 @@ def conv3x3_relu(xs, B, H, W, Cin, conv, want_f32=False, want_split=True):
     ev0 = _prof_begin()
     with torch.cuda.device(dev):
         rc = _c.load().mb200_conv3x3_bf16x3(_c.ptr(xs[0]), _c.ptr(xs[1]), _c.ptr(wsp.hi), _c.ptr(wsp.lo), B, H, W, Cin,
-                                            Cout, _c.ptr(conv.bias.detach()) if conv.bias is not None else None, 1,
+                                            Cout, _c.ptr(conv.bias.detach()) if conv.bias is not None else None,
+                                            1 if relu else 0,
                                             _c.ptr(y), _c.ptr(yh), _c.ptr(yl), _c.cur_stream())
     _c.check(rc, "mb200_conv3x3_bf16x3")
     _prof_end("conv3x3", 2.0 * B * H * W * Cout * 9 * Cin, ev0)

@@ -326,21 +326,49 @@ def filter_det(scores, boxes, start_ind=0, max_per_img=100, thresh=0.001, pre_nm
     return torch.from_numpy(inds[idx] + start_ind), torch.from_numpy(sa[idx]), torch.from_numpy(la[idx])
 
 
+def load_resnet():
+    """lib/object_detector.py:615-620: torchvision resnet101 minus layer4 / avgpool / fc (third-party arithmetic
+    boundary, SURVEY.md section 8c: the architecture comes from torchvision here as it does in the reference)."""
+    from torchvision.models.resnet import resnet101
+    model = resnet101(weights=None)
+    del model.layer4
+    del model.avgpool
+    del model.fc
+    return model
+
+
 class ObjectDetector(nn.Module):
-    def __init__(self, classes, mode='gtbox', max_per_img=64, thresh=0.05):
+    def __init__(self, classes, mode='gtbox', max_per_img=64, thresh=0.05, use_resnet=False):
         super().__init__()
         self.classes, self.mode, self.max_per_img, self.thresh = classes, mode, max_per_img, thresh
-        vgg = load_vgg()
-        self.features, self.roi_fmap = vgg.features, vgg.classifier
-        self.score_fc = nn.Linear(4096, len(classes))
-        self.bbox_fc = nn.Linear(4096, len(classes) * 4)
-        self.rpn_head = RPNHead(512, 512)
+        self.use_resnet = use_resnet
+        if not use_resnet:
+            vgg = load_vgg()
+            self.features, self.roi_fmap = vgg.features, vgg.classifier
+            rpn_input_dim, output_dim = 512, 4096
+        else:                               # lib/object_detector.py:84-101 ("Deprecated" there, BASELINE config 3)
+            self.features = load_resnet()
+            self.compress = nn.Sequential(nn.Conv2d(1024, 256, kernel_size=1), nn.ReLU(inplace=True), nn.BatchNorm2d(256))
+            self.roi_fmap = nn.Sequential(nn.Linear(256 * 7 * 7, 2048), nn.SELU(inplace=True), nn.AlphaDropout(p=0.05),
+                                          nn.Linear(2048, 2048), nn.SELU(inplace=True), nn.AlphaDropout(p=0.05))
+            rpn_input_dim, output_dim = 1024, 2048
+        self.score_fc = nn.Linear(output_dim, len(classes))
+        self.bbox_fc = nn.Linear(output_dim, len(classes) * 4)
+        self.rpn_head = RPNHead(512, rpn_input_dim)
         self.masks = None
         self.rng = np.random
 
+    def feature_map(self, x):
+        """lib/object_detector.py:110-127."""
+        if not self.use_resnet:
+            return self.features(x)
+        f = self.features
+        x = f.maxpool(f.relu(f.bn1(f.conv1(x))))
+        return f.layer3(f.layer2(f.layer1(x)))
+
     def forward(self, x, im_sizes, image_offset, gt_boxes=None, gt_classes=None, gt_rels=None):
         with torch.no_grad():
-            fmap = self.features(x)
+            fmap = self.feature_map(x)
             rel_labels = obj_labels = None
             if self.mode == 'gtbox':
                 im_inds = gt_classes[:, 0] - image_offset
@@ -350,7 +378,7 @@ class ObjectDetector(nn.Module):
                 obj_labels = gt_classes[:, 1]
             else:
                 rois = self.rpn_head.roi_proposals(self.rpn_head(fmap), im_sizes)
-            pool = roi_align(fmap, rois)
+            pool = roi_align(self.compress(fmap) if self.use_resnet else fmap, rois)        # :136-137
             obj_fmap = run_classifier(self.roi_fmap, pool.view(rois.size(0), -1), self.masks, "roi_fmap.")
             od_obj_dists = self.score_fc(obj_fmap)
             if self.mode == 'gtbox':
