@@ -157,8 +157,14 @@ class ObjectDetector(nn.Module):
         """[B,3,S,S] -> stride-16 map [B,512,S/16,S/16] (object_detector.py:110-127). The map lives in
         NHWC; the returned tensor is its NCHW view (same memory)."""
         if any(p.requires_grad for p in self.features.parameters()) and torch.is_grad_enabled():
-            raise NotImplementedError("backbone training (models/train_detector.py) is not built yet: the "
-                                      "tcgen05 convolution is forward only (SURVEY.md §8f f1)")
+            if self.use_resnet or os.environ.get("MOTIFS_EXPERIMENTAL_DETECTOR_TRAIN", "0") != "1":
+                raise NotImplementedError("backbone training (models/train_detector.py, SURVEY.md §8f f1): the "
+                                          "gradient path (lib/conv_tc.py) is pinned on the CPU but has not run on a "
+                                          "B200 yet — set MOTIFS_EXPERIMENTAL_DETECTOR_TRAIN=1 to use it (VGG only)")
+            from lib import conv_tc
+            nhwc = conv_tc.vgg_features_train(x.contiguous().float(), self._convs(), tc_ops.VGG16_CFG)
+            self._fmap_nhwc, self._fmap_split = None, None       # consumers take the autograd paths
+            return nhwc.permute(0, 3, 1, 2)
         with torch.no_grad():
             need_split = self.mode in ('rpntrain', 'refinerels')
             if self.use_resnet:         # conv1 .. layer3 (:119-127) walked on the kernels, NHWC [B,37,37,1024]
@@ -417,6 +423,18 @@ class RPNHead(nn.Module):
         the tcgen05 implicit GEMM and the 1x1 conv is a plain GEMM whose output is already NHWC
         (the reference transposes NCHW->NHWC here, :551-558)."""
         B, C, h, w = fmap.shape
+        c0 = self.conv[0]
+        if torch.is_grad_enabled() and (fmap.requires_grad or c0.weight.requires_grad):
+            # training the head (models/train_detector.py): the forward-only kernel call below would silently drop
+            # the gradients of conv[0] and of the feature map
+            if os.environ.get("MOTIFS_EXPERIMENTAL_DETECTOR_TRAIN", "0") != "1":
+                raise NotImplementedError("RPN head training (SURVEY.md §8f f1) needs the experimental gradient path: "
+                                          "set MOTIFS_EXPERIMENTAL_DETECTOR_TRAIN=1 (lib/conv_tc.py)")
+            from lib import conv_tc
+            y = conv_tc.conv3x3(fmap.permute(0, 2, 3, 1).contiguous(), c0.weight, c0.bias, relu=True).clamp(max=6.0)
+            c1 = self.conv[2]
+            rez = tc_ops.linear_tc(y.view(B * h * w, -1), c1.weight.view(c1.weight.size(0), -1), c1.bias)
+            return rez.view(B, h, w, self._A, self.anchor_target_dim)
         if fmap_split is None:
             xs = tc_ops.split_rows(fmap.detach().permute(0, 2, 3, 1).reshape(-1, C))
             fmap_split = (xs.hi.view(B, h, w, C), xs.lo.view(B, h, w, C))
