@@ -212,14 +212,13 @@ def run_b200(args):
         torch.cuda.synchronize(); t0 = time.perf_counter()
         train_step(model, opt, reducer, fwd_tuple=resident[extra % len(resident)])
         torch.cuda.synchronize(); recent.append(time.perf_counter() - t0); extra += 1
-        if len(recent) >= 12 and max(recent[-5:]) <= 1.03 * min(recent[-5:]) and min(recent[-5:]) <= 1.03 * min(recent):
+        settled = len(recent) >= 12 and max(recent[-5:]) <= 1.03 * min(recent[-5:]) and min(recent[-5:]) <= 1.03 * min(recent)
+        if world > 1:       # train_step holds collectives: every rank must leave this loop in the same iteration
+            flag = torch.tensor([1 if settled else 0], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            settled = bool(flag.item())
+        if settled:
             break
-    if world > 1:       # every rank must leave the warm-up after the same number of steps
-        n_extra = torch.tensor([extra], device=dev)
-        dist.all_reduce(n_extra, op=dist.ReduceOp.MAX)
-        for i in range(int(n_extra.item()) - extra):
-            train_step(model, opt, reducer, fwd_tuple=resident[i % len(resident)])
-        extra = int(n_extra.item())
     W += extra
     # Python's cyclic GC pauses the host for tens of ms when a generation-2 pass lands in a step (seen as one
     # 90 ms step among 21.7 ms ones): collect now, freeze what survived, and keep the collector off inside the
