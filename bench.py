@@ -145,6 +145,29 @@ def train_step(model, optimizer, reducer=None, fwd_tuple=None, blob=None):
     return float(loss.detach())  # the reference's train_batch reads the losses back every step (train_rels.py:151)
 
 
+def settle_warmup(step, sync, world, dev, min_steps=12, max_steps=60, tol=1.03):
+    """Untimed warm-up steps until the step time has settled: at least `min_steps`, then the last five within
+    `tol` of each other and of the best, or `max_steps`. `step(i)` may hold collectives (the gradient all-reduce),
+    so with world > 1 the decision to stop is itself collective: every rank leaves in the same iteration.
+    Returns the number of steps run."""
+    import torch
+    import torch.distributed as dist
+    recent, n = [], 0
+    while n < max_steps:
+        sync(); t0 = time.perf_counter()
+        step(n)
+        sync(); recent.append(time.perf_counter() - t0); n += 1
+        settled = len(recent) >= min_steps and max(recent[-5:]) <= tol * min(recent[-5:]) and \
+            min(recent[-5:]) <= tol * min(recent)
+        if world > 1:
+            flag = torch.tensor([1 if settled else 0], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            settled = bool(flag.item())
+        if settled:
+            break
+    return n
+
+
 # ------------------------------------------------------------------------------------------ b200 arm
 def run_b200(args):
     import torch
@@ -207,18 +230,8 @@ def run_b200(args):
         train_step(model, opt, reducer, fwd_tuple=resident[i % len(resident)])
     # A fresh box keeps paging libraries in and autotuning for a while: keep warming up (untimed) until
     # the step time has settled — at least 12 extra steps and the last five within 3 % of each other and of the best — or 60 extra steps.
-    recent, extra = [], 0
-    while extra < 60:
-        torch.cuda.synchronize(); t0 = time.perf_counter()
-        train_step(model, opt, reducer, fwd_tuple=resident[extra % len(resident)])
-        torch.cuda.synchronize(); recent.append(time.perf_counter() - t0); extra += 1
-        settled = len(recent) >= 12 and max(recent[-5:]) <= 1.03 * min(recent[-5:]) and min(recent[-5:]) <= 1.03 * min(recent)
-        if world > 1:       # train_step holds collectives: every rank must leave this loop in the same iteration
-            flag = torch.tensor([1 if settled else 0], device=dev)
-            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-            settled = bool(flag.item())
-        if settled:
-            break
+    extra = settle_warmup(lambda i: train_step(model, opt, reducer, fwd_tuple=resident[i % len(resident)]),
+                          torch.cuda.synchronize, world, dev)
     W += extra
     # Python's cyclic GC pauses the host for tens of ms when a generation-2 pass lands in a step (seen as one
     # 90 ms step among 21.7 ms ones): collect now, freeze what survived, and keep the collector off inside the

@@ -180,3 +180,37 @@ def test_flat_sgd_direct_gradient_writes_gloo_world2():
         assert torch.allclose(out[1][i], avg, atol=1e-6), i
         for r in (0, 1):        # second backward added this rank's own gradient on top (no overwrite)
             assert torch.allclose(out[20 + r][i], out[10 + r][i], atol=1e-6), (r, i)
+
+
+def _worker_settle(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import sys
+    import time
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root); sys.path.insert(0, os.path.join(root, "neural-motifs_b200"))
+    import bench
+    from lib.data_parallel import init_from_env
+    init_from_env("gloo")
+    import random
+    rnd = random.Random(rank)
+    steps = []
+
+    def step(i):                                  # a step with a collective inside and rank-dependent timing noise
+        time.sleep(0.004 + (0.004 * rnd.random() if (rank == 1 and i < 20) else 0.0))
+        t = torch.ones(4)
+        dist.all_reduce(t)
+        steps.append(i)
+
+    n = bench.settle_warmup(step, lambda: None, world, torch.device("cpu"), min_steps=6, max_steps=40, tol=1.5)
+    out[rank] = (n, len(steps))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_bench_settle_warmup_leaves_collectively_gloo_world2():
+    """bench.py's adaptive warm-up: ranks with different timing noise must run the SAME number of steps (each step
+    holds the gradient all-reduce; a rank leaving early would pair its next collective with the others' all-reduce)."""
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker_settle, args=(2, _free_port(), out), nprocs=2, join=True)
+    assert out[0] == out[1] and 6 <= out[0][0] <= 40
