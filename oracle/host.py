@@ -182,14 +182,18 @@ def rel_assignments(im_inds, rois, roi_gtlabels, gt_boxes, gt_classes, gt_rels, 
     return np.concatenate(rel_labels, 0)
 
 
-def proposal_assignments_det(rois, gt_boxes, gt_classes, image_offset, rng, fg_thresh=0.5):
+def proposal_assignments_det(rois, gt_boxes, gt_classes, image_offset, rng, fg_thresh=0.5, order=None):
     """lib/fpn/proposal_assignments/proposal_assignments_det.py:12-117 on numpy arrays (fp32 IoU as the
-    torch branch of box_utils.bbox_overlaps). Returns (rois [n,5] f32, labels [n] i64, targets [n,4] f32)."""
+    torch branch of box_utils.bbox_overlaps). Returns (rois [n,5] f32, labels [n] i64, targets [n,4] f32).
+    The reference orders the candidates with `torch.sort(ims_per_box, 0)` (:33), whose order among equal image
+    indices is implementation-defined (torch 2.11's CPU sort is NOT stable there); this restatement and the product
+    use the stable order. `order` injects a given permutation so that the fixture produced by running the reference
+    (tests/golden/make_golden_host2.py stores the permutation its torch.sort returned) can be matched exactly."""
     fg_per = int(np.round(256 * 0.25))
     gt_img = gt_classes[:, 0] - image_offset
     all_boxes = np.concatenate([rois[:, 1:], gt_boxes], 0).astype(np.float32)
     ims = np.concatenate([rois[:, 0].astype(np.int64), gt_img], 0)
-    idx = np.argsort(ims, kind="stable")
+    idx = np.argsort(ims, kind="stable") if order is None else np.asarray(order)
     im_sorted, all_boxes = ims[idx], all_boxes[idx]
     out_r, out_l, out_t = [], [], []
     for im in range(int(im_sorted[-1]) + 1):

@@ -1,0 +1,108 @@
+"""Pins of the oracle restatements — and of the product's host functions that run on CPU tensors — against fixtures
+produced by RUNNING THE REFERENCE's own code in the build container (tests/golden/make_golden_host2.py ->
+reference_host_ops2.npz): proposal_assignments_gtbox / _det with the numpy RNG consumed in the reference's order,
+surgery.filter_dets, rel_model._sort_by_score (the reference holds no golden vectors for this path,
+so outputs of the reference itself are the pin)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "neural-motifs_b200"))
+
+
+@pytest.fixture(scope="module")
+def g2():
+    return np.load(os.path.join(ROOT, "tests", "golden", "reference_host_ops2.npz"))
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_proposal_assignments_gtbox_oracle_and_product_match_reference(g2, tag):
+    from oracle import model as OM
+    from lib.fpn.proposal_assignments.proposal_assignments_gtbox import proposal_assignments_gtbox
+    off, seed = [int(v) for v in g2["gtbox_%s_meta" % tag]]
+    rois, gt_boxes, gt_classes, gt_rels = (torch.from_numpy(g2["gtbox_%s_%s" % (tag, k)])
+                                           for k in ("rois", "gt_boxes", "gt_classes", "gt_rels"))
+    want = torch.from_numpy(g2["gtbox_%s_rel_labels" % tag])
+    got_o = OM.proposal_assignments_gtbox(rois, gt_boxes, gt_classes, gt_rels, off, np.random.RandomState(seed))
+    assert torch.equal(got_o, want)
+    _, labels, got_p = proposal_assignments_gtbox(rois, gt_boxes, gt_classes, gt_rels, off, rng=np.random.RandomState(seed))
+    assert torch.equal(got_p, want)
+    assert np.array_equal(labels.numpy(), g2["gtbox_%s_labels" % tag])
+
+
+def test_proposal_assignments_det_oracle_matches_reference(g2):
+    """Exact match once the oracle is given the candidate order the reference's (unstable) torch.sort produced; with
+    its own stable order the same rule set applies (same counts of foreground / background rows per image)."""
+    from oracle import host
+    off, seed = [int(v) for v in g2["det_meta"]]
+    args = (g2["det_rois"], g2["det_gt_boxes"], g2["det_gt_classes"], off)
+    r, l, t = host.proposal_assignments_det(*args, np.random.RandomState(seed), order=g2["det_sort_idx"])
+    assert np.array_equal(r, g2["det_out_rois"]) and np.array_equal(l, g2["det_out_labels"])
+    assert np.array_equal(t, g2["det_out_targets"])
+    r2, l2, t2 = host.proposal_assignments_det(*args, np.random.RandomState(seed))
+    assert r2.shape == r.shape
+    for im in range(2):
+        assert int(((r2[:, 0] == im) & (l2 > 0)).sum()) == int(((r[:, 0] == im) & (l > 0)).sum())
+
+
+def test_filter_dets_order_matches_reference(g2):
+    """surgery.py:21-59: relations sorted by (best non-background predicate) x obj score x obj score, descending."""
+    obj_scores, pred_scores, rel_inds = g2["fd_in_obj_scores"], g2["fd_in_pred_scores"], g2["fd_in_rel_inds"]
+    key = pred_scores[:, 1:].max(1) * obj_scores[rel_inds[:, 0]] * obj_scores[rel_inds[:, 1]]
+    order = np.argsort(-key, kind="stable")
+    assert np.array_equal(rel_inds[order], g2["fd_out_rels"])
+    assert np.array_equal(pred_scores[order], g2["fd_out_pred_scores"])
+    assert np.array_equal(g2["fd_out_boxes"], g2["fd_in_boxes"]) and np.array_equal(g2["fd_out_objs"], g2["fd_in_obj_classes"])
+    # the oracle's inlined version (oracle/model.py, end of RelModel.forward) is the same expression in torch
+    s = torch.from_numpy(obj_scores); ri = torch.from_numpy(rel_inds); rr = torch.from_numpy(pred_scores)
+    _, idx = torch.sort((rr[:, 1:].max(1)[0] * s[ri[:, 0]] * s[ri[:, 1]]).view(-1), dim=0, descending=True, stable=True)
+    assert np.array_equal(ri[idx].numpy(), g2["fd_out_rels"])
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c", "d"])
+def test_sort_by_score_oracle_and_product_match_reference(g2, tag):
+    from oracle import model as OM
+    from lib.rel_model import _sort_by_score
+    im = torch.from_numpy(g2["sort_%s_im" % tag]); scores = torch.from_numpy(g2["sort_%s_scores" % tag])
+    for fn in (OM.sort_by_score, _sort_by_score):
+        perm, inv, ls = fn(im, scores)
+        assert list(ls) == g2["sort_%s_ls" % tag].tolist()
+        if tag == "d":      # two equal scores inside an image: the reference's torch.sort leaves their order unspecified
+            want = g2["sort_%s_perm" % tag]
+            assert np.array_equal(scores.numpy()[perm.numpy()], scores.numpy()[want])
+            assert np.array_equal(im.numpy()[perm.numpy()], im.numpy()[want])
+            assert np.array_equal(np.sort(perm.numpy()), np.arange(len(want)))
+            continue
+        assert np.array_equal(inv.numpy(), g2["sort_%s_inv" % tag]) and np.array_equal(perm.numpy(), g2["sort_%s_perm" % tag])
+    perm, inv, ls = _sort_by_score(im, scores, host=g2["sort_%s_im" % tag])
+    assert np.array_equal(scores.numpy()[perm.numpy()], scores.numpy()[g2["sort_%s_perm" % tag]])
+
+
+def test_decoder_rnn_oracle_matches_reference_module():
+    """oracle/model.py:DecoderRNN against the REFERENCE's lib/lstm/decoder_rnn.py run on the CPU
+    (tests/golden/make_golden_decoder.py): teacher-forced training forward with background labels, and greedy eval
+    with the overlap-aware commitment loop (the fixture's commitments differ from plain greedy ones)."""
+    from oracle import model as OM
+    g = np.load(os.path.join(ROOT, "tests", "golden", "reference_decoder.npz"))
+    H, D = [int(v) for v in g["dims"]]
+    classes = ['__background__'] + ['c%d' % i for i in range(150)]
+    dec = OM.DecoderRNN(classes, D, H)
+    dec.load_state_dict({k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd_")})
+    dec.train()
+    dists, commits = dec(torch.from_numpy(g["tr_x"]), g["tr_bl"].tolist(), labels=torch.from_numpy(g["tr_labels"]))
+    assert np.array_equal(commits.numpy(), g["tr_commits"])
+    assert np.allclose(dists.detach().numpy(), g["tr_dists"], rtol=1e-5, atol=1e-6)
+    dec.eval()
+    T = g["ev_x"].shape[0]
+    with torch.no_grad():
+        dists, commits = dec(torch.from_numpy(g["ev_x"]), [1] * T, boxes_for_nms=torch.from_numpy(g["ev_boxes"]))
+        _, greedy = dec(torch.from_numpy(g["ev_x"]), [1] * T)
+    assert np.allclose(dists.numpy(), g["ev_dists"], rtol=1e-5, atol=1e-6)
+    assert np.array_equal(commits.numpy(), g["ev_commits"])
+    assert np.array_equal(greedy.numpy(), g["ev_commits_greedy"])
+    assert not np.array_equal(g["ev_commits"], g["ev_commits_greedy"])
