@@ -106,3 +106,17 @@ def test_decoder_rnn_oracle_matches_reference_module():
     assert np.array_equal(commits.numpy(), g["ev_commits"])
     assert np.array_equal(greedy.numpy(), g["ev_commits_greedy"])
     assert not np.array_equal(g["ev_commits"], g["ev_commits_greedy"])
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_rel_assignments_oracle_and_product_match_reference(tag):
+    """SGDet-training relation labels (rel_assignments.py:15-145) with the numpy RNG consumed in the reference's
+    order: foreground sampling proportional to IoU products, background sampling, per-image lexsort."""
+    from oracle import host
+    g = np.load(os.path.join(ROOT, "tests", "golden", "reference_rel_assignments.npz"))
+    off, seed, nsg, fno = [int(v) for v in g["ra_%s_meta" % tag]]
+    a = {k: g["ra_%s_%s" % (tag, k)] for k in ("ims", "boxes", "labels", "gt_boxes", "gt_classes", "gt_rels", "out")}
+    got = host.rel_assignments(a["ims"], a["boxes"], a["labels"], a["gt_boxes"], a["gt_classes"], a["gt_rels"], off,
+                               np.random.RandomState(seed), num_sample_per_gt=nsg, filter_non_overlap=bool(fno))
+    assert np.array_equal(got, a["out"])
+    assert int((a["out"][:, 3] > 0).sum()) > 0            # the fixture holds foreground relations
