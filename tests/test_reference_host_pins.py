@@ -120,3 +120,34 @@ def test_rel_assignments_oracle_and_product_match_reference(tag):
                                np.random.RandomState(seed), num_sample_per_gt=nsg, filter_non_overlap=bool(fno))
     assert np.array_equal(got, a["out"])
     assert int((a["out"][:, 3] > 0).sum()) > 0            # the fixture holds foreground relations
+
+
+def test_forward_tuple_layout_matches_reference_blob():
+    """dataloaders/synthetic.py hands `RelModel.forward` the same positional tuple the reference's Blob produces from
+    the same images / boxes / relations (blob.py:62-229 run on the CPU, tests/golden/make_golden_blob.py): gt_classes
+    rows = (image index within the batch, class), gt_rels rows = (image, subject, object, predicate) with box indices
+    local to the image, im_sizes rows = (h, w, scale), image_offset 0 on a single GPU; and the training tuple's
+    train_anchor_inds = (image, h, w, anchor) rows of anchor_target_layer, per image in order."""
+    from dataloaders.synthetic import to_tuple, SyntheticBlob
+    from oracle.host import anchor_target_layer        # the product's runs its IoU on the GPU (parity-tested there)
+    g = np.load(os.path.join(ROOT, "tests", "golden", "reference_blob.npz"))
+    nb = dict(imgs=g["nb_imgs"], im_sizes=g["nb_im_sizes"], image_offset=0, gt_boxes=g["nb_gt_boxes"],
+              gt_classes=g["nb_gt_classes"], gt_rels=g["nb_gt_rels"])
+    for tup in (to_tuple(nb, "cpu"), (lambda b: (b.scatter(), b[0])[1])(SyntheticBlob(nb, "cpu"))):
+        assert len(tup) == 8 and tup[6] is None
+        for tag in ("train", "eval"):
+            assert np.array_equal(tup[0].numpy(), g[tag + "_imgs"])
+            assert np.array_equal(np.asarray(tup[1], dtype=np.float64), np.asarray(g[tag + "_im_sizes"], dtype=np.float64))
+            assert int(tup[2]) == int(g[tag + "_image_offset"]) == 0
+            assert np.array_equal(tup[3].numpy(), g[tag + "_gt_boxes"]) and tup[3].dtype == torch.float32
+            assert np.array_equal(tup[4].numpy(), g[tag + "_gt_classes"]) and tup[4].dtype == torch.int64
+            assert np.array_equal(tup[5].numpy(), g[tag + "_gt_rels"]) and tup[5].dtype == torch.int64
+    # train_anchor_inds: the reference calls anchor_target_layer per appended image with the global numpy RNG
+    np.random.seed(5)
+    rows = []
+    for i in range(3):
+        gb = nb["gt_boxes"][nb["gt_classes"][:, 0] == i]
+        h, w = nb["im_sizes"][i][:2]
+        _, inds, _, _ = anchor_target_layer(gb, (h, w), rng=np.random)
+        rows.append(np.column_stack((np.full(inds.shape[0], i, dtype=np.int64), inds)))
+    assert np.array_equal(np.concatenate(rows, 0), g["train_anchor_inds"])
