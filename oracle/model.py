@@ -5,11 +5,15 @@ lib/rel_model.py (`_sort_by_score` :31-61, `LinearizedContext` :66-296, `RelMode
 lib/lstm/decoder_rnn.py (:40-251), lib/get_union_boxes.py (:15-93), lib/sparse_targets.py (:32-37),
 lib/surgery.py (:21-59), lib/fpn/proposal_assignments/proposal_assignments_gtbox.py (:9-87).
 
-The reference itself cannot run here (PyTorch 0.3 API, CUDA-only operators, needs VG data — SURVEY.md
-§8c): PARITY OF THE MODEL-LEVEL FORWARD IS UNPINNED by reference outputs; the operator-level pieces it
-is assembled from are pinned (oracle/ops.py, oracle/highway_lstm.py). Module and parameter names equal
-the reference's, so one state dict drives the oracle and the product. All randomness (dropout
-masks, sampling RNG) is injected."""
+PINNING. The reference cannot run as shipped here (PyTorch 0.3 API, CUDA-only operators, needs VG data — SURVEY.md
+§8c), but its own model code CAN be executed on the CPU once its three CUDA extensions are replaced by the operator
+restatements of oracle/ops.py / oracle/highway_lstm.py (themselves pinned on the GPU against the reference's .cu
+files) and PyTorch-0.3 semantics are shimmed: tests/golden/make_golden_model.py does that, and
+tests/test_reference_model_pin.py holds this file to the outputs of the reference's RelModel — PredCls / SGCls /
+SGDet eval tuples and an SGCls training forward + backward (logits 1e-4, loss, gradients of every trainable
+parameter 1e-3) — with both sides loading the same synthetic state dict (same keys and shapes).
+Module and parameter names equal the reference's, so one state dict drives the reference, the oracle and the
+product. All randomness (dropout masks, sampling RNG) is injected."""
 import math
 
 import numpy as np

@@ -1,0 +1,123 @@
+"""MODEL-LEVEL pin: the oracle's RelModel against the REFERENCE's own RelModel executed on the CPU in the build
+container (tests/golden/make_golden_model.py): every Python line of the reference model ran — context construction,
+sorting / packing, decoder loop, union-box branch, relation tail, frequency bias, filter_dets — with its three CUDA
+extensions replaced by the oracle's operator restatements (pinned separately on the GPU against the reference's .cu
+files) and GloVe / VG / ImageNet tables replaced by seeded synthetic values. Both sides load the same synthetic state
+dict, regenerated from (name, shape, seed) by tests/golden/synthetic_state.py; the fixture holds the reference's
+state-dict keys / shapes and its eval outputs for BASELINE config 1 (one 592x592 image, 20 GT boxes, 380 pairs)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "neural-motifs_b200"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+@pytest.mark.parametrize("mode", ["predcls", "sgcls"])
+def test_oracle_relmodel_eval_matches_reference_relmodel(mode):
+    from oracle import model as OM
+    from golden.synthetic_state import synthetic_state, CLASSES, RELS, KW, make_inputs
+    g = np.load(os.path.join(ROOT, "tests", "golden", "reference_model_eval.npz"))
+    orc = OM.RelModel(CLASSES, RELS, mode=mode, **KW)
+    sd = orc.state_dict()
+    ref_keys = [str(k) for k in g[mode + "_keys"]]
+    ref_shapes = {k: tuple(int(v) for v in s.split(";") if v) for k, s in zip(ref_keys, g[mode + "_shapes"])}
+    # the reference's state dict and the oracle's (= the product's) are interchangeable: same keys, same shapes
+    assert set(sd.keys()) == set(ref_keys), (set(sd) ^ set(ref_keys))
+    assert all(tuple(sd[k].shape) == ref_shapes[k] for k in ref_keys)
+    orc.load_state_dict(synthetic_state([(k, ref_shapes[k], sd[k].dtype) for k in ref_keys], seed=3))
+    orc.eval()
+    nb = make_inputs(seed=11)
+    t = torch.from_numpy
+    with torch.no_grad():
+        boxes, objs, obj_scores, rels, pred_scores = orc(t(nb["imgs"]), nb["im_sizes"], 0, t(nb["gt_boxes"]),
+                                                         t(nb["gt_classes"]), t(nb["gt_rels"]))
+    assert np.array_equal(np.asarray(boxes), g[mode + "_boxes"])
+    assert np.array_equal(np.asarray(objs), g[mode + "_objs"])
+    assert np.allclose(np.asarray(obj_scores), g[mode + "_obj_scores"], rtol=1e-4, atol=1e-6)
+    want_rels, want_scores = g[mode + "_rels"], g[mode + "_pred_scores"]
+    assert np.asarray(rels).shape == want_rels.shape == (380, 2)
+    # same relation -> same predicate distribution (order-independent), then the ranking itself
+    key = lambda r: r[:, 0] * 1000 + r[:, 1]
+    a, b = np.argsort(key(np.asarray(rels))), np.argsort(key(want_rels))
+    assert np.array_equal(np.asarray(rels)[a], want_rels[b])
+    err = np.abs(np.asarray(pred_scores)[a] - want_scores[b]).max()
+    assert err < 1e-4 * max(1.0, float(np.abs(want_scores).max())), err
+    assert (np.asarray(rels) == want_rels).all(1).mean() > 0.98      # ranking equal up to near-ties of the sort key
+
+
+def test_oracle_relmodel_sgcls_train_forward_matches_reference_relmodel():
+    """Training forward (models/train_rels.py:118-141): GT-box relation sampling, training-mode BatchNorm in the
+    position embedding and the union-box branch, teacher-forced decoder, the two cross-entropies; dropout off on both
+    sides (the reference draws its masks from torch's RNG inside nn.Dropout, the oracle takes injected masks)."""
+    import torch.nn.functional as F
+    from oracle import model as OM
+    from golden.synthetic_state import synthetic_state, CLASSES, RELS, KW, make_inputs
+    from model_utils import make_masks
+    g = np.load(os.path.join(ROOT, "tests", "golden", "reference_model_train.npz"))
+    orc = OM.RelModel(CLASSES, RELS, mode="sgcls", **KW)
+    sd = orc.state_dict()
+    orc.load_state_dict(synthetic_state([(k, tuple(v.shape), v.dtype) for k, v in sd.items()], seed=3))
+    orc.train()
+    nb = make_inputs(seed=12, boxes=14, rels=9)
+    n_obj, n_rel = 14, g["train_rel_labels"].shape[0]
+    det, top, ctx = make_masks(n_obj, n_rel, 1, seed=0)
+    ones = lambda d: {k: torch.ones_like(v) for k, v in d.items()}
+    orc.detector.masks, orc.masks, orc.context.masks = ones(det), ones(top), ones(ctx)
+    orc.detector.rng = np.random.RandomState(21)
+    t = torch.from_numpy
+    res = orc(t(nb["imgs"]), nb["im_sizes"], 0, t(nb["gt_boxes"]), t(nb["gt_classes"]), t(nb["gt_rels"]))
+    assert np.array_equal(res.rel_labels.numpy(), g["train_rel_labels"])
+    assert np.array_equal(res.rm_obj_labels.numpy(), g["train_rm_obj_labels"])
+    for k, tol in (("rm_obj_dists", 1e-4), ("rel_dists", 1e-4)):
+        got, want = getattr(res, k).detach().numpy(), g["train_" + k]
+        assert np.abs(got - want).max() < tol * max(1.0, float(np.abs(want).max())), (k, np.abs(got - want).max())
+    loss = F.cross_entropy(res.rm_obj_dists, res.rm_obj_labels) + F.cross_entropy(res.rel_dists, res.rel_labels[:, -1])
+    assert abs(float(loss) - float(g["train_loss"])) < 1e-4 * float(g["train_loss"])
+    assert np.allclose(orc.union_boxes.conv[2].running_mean.numpy(), g["train_bn_running_mean"], rtol=1e-4, atol=1e-6)
+    # backward: every trainable parameter of the reference model received a gradient; norms and 16 samples each agree
+    for p_ in orc.detector.parameters():
+        p_.requires_grad = False
+    loss.backward()
+    grads = {k: p_.grad for k, p_ in orc.named_parameters() if p_.grad is not None}
+    names = [str(k) for k in g["train_grad_names"]]
+    assert set(names) == set(grads), set(names) ^ set(grads)
+    for k, norm, samp in zip(names, g["train_grad_norms"], g["train_grad_samples"]):
+        gf = grads[k].reshape(-1)
+        idx = (torch.arange(16) * (gf.numel() - 1)) // 15
+        assert abs(float(gf.double().norm()) - norm) < 1e-3 * max(norm, 1e-8), (k, float(gf.double().norm()), norm)
+        assert np.abs(gf[idx].numpy() - samp).max() < 1e-3 * max(float(np.abs(samp).max()), float(norm) / gf.numel() ** 0.5, 1e-9), k
+
+
+def test_oracle_relmodel_sgdet_eval_matches_reference_relmodel():
+    """SGDet eval: RPN head, proposal decode + NMS, detector heads, per-class NMS to 64 detections, overlapping pairs,
+    context with the decoder's overlap-aware commitments, relation tail, filter_dets (detector threshold 0)."""
+    from oracle import model as OM
+    from golden.synthetic_state import synthetic_state, CLASSES, RELS, KW, make_inputs
+    g = np.load(os.path.join(ROOT, "tests", "golden", "reference_model_eval.npz"))
+    orc = OM.RelModel(CLASSES, RELS, mode="sgdet", thresh=0.0, **KW)
+    sd = orc.state_dict()
+    ref_keys = [str(k) for k in g["sgdet_keys"]]
+    assert set(sd.keys()) == set(ref_keys), (set(sd) ^ set(ref_keys))
+    orc.load_state_dict(synthetic_state([(k, tuple(sd[k].shape), sd[k].dtype) for k in ref_keys], seed=3))
+    orc.eval()
+    nb = make_inputs(seed=11)
+    with torch.no_grad():
+        boxes, objs, obj_scores, rels, pred_scores = orc(torch.from_numpy(nb["imgs"]), nb["im_sizes"], 0)
+    assert np.asarray(boxes).shape == g["sgdet_boxes"].shape == (64, 4)
+    assert np.abs(np.asarray(boxes) - g["sgdet_boxes"]).max() < 1e-2            # pixels, after exp() of the regressed deltas
+    assert np.array_equal(np.asarray(objs), g["sgdet_objs"])
+    assert np.allclose(np.asarray(obj_scores), g["sgdet_obj_scores"], rtol=1e-3, atol=1e-6)
+    want_rels, want_scores = g["sgdet_rels"], g["sgdet_pred_scores"]
+    assert np.asarray(rels).shape == want_rels.shape
+    key = lambda r: r[:, 0] * 1000 + r[:, 1]
+    a, b = np.argsort(key(np.asarray(rels))), np.argsort(key(want_rels))
+    assert np.array_equal(np.asarray(rels)[a], want_rels[b])                    # the same candidate pairs
+    err = np.abs(np.asarray(pred_scores)[a] - want_scores[b]).max()
+    assert err < 1e-3 * max(1.0, float(np.abs(want_scores).max())), err
+    assert (np.asarray(rels) == want_rels).all(1).mean() > 0.95
