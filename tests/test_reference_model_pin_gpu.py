@@ -1,0 +1,44 @@
+"""The PRODUCT on the GPU against the outputs of the REFERENCE's own RelModel (tests/golden/reference_model_eval.npz,
+produced by tests/golden/make_golden_model.py; see tests/test_reference_model_pin.py for what ran there). Written at
+the end of round 1 without GPU budget left to run it, hence gated: set MOTIFS_REFERENCE_PIN_GPU=1. (The ungated chain
+is reference -> oracle on the CPU, oracle -> product in tests/test_model_gpu.py.)"""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("MOTIFS_REFERENCE_PIN_GPU", "0") != "1",
+                                 reason="not yet run on a B200: set MOTIFS_REFERENCE_PIN_GPU=1")]
+
+
+@pytest.mark.parametrize("mode", ["predcls", "sgcls"])
+def test_product_eval_matches_reference_relmodel_outputs(cuda, mode):
+    from lib.rel_model import RelModel
+    from golden.synthetic_state import synthetic_state, CLASSES, RELS, KW, make_inputs
+    g = np.load(os.path.join(ROOT, "tests", "golden", "reference_model_eval.npz"))
+    prod = RelModel(CLASSES, RELS, mode=mode, num_gpus=1, require_overlap_det=True, use_resnet=False, use_proposals=False,
+                    pass_in_obj_feats_to_decoder=False, pass_in_obj_feats_to_edge=False, rec_dropout=0.1, **KW)
+    sd = prod.state_dict()
+    ref_keys = [str(k) for k in g[mode + "_keys"]]
+    assert set(sd.keys()) == set(ref_keys), (set(sd) ^ set(ref_keys))
+    prod.load_state_dict(synthetic_state([(k, tuple(sd[k].shape), sd[k].dtype) for k in ref_keys], seed=3))
+    prod = prod.to(cuda).eval()
+    nb = make_inputs(seed=11)
+    t = lambda a: torch.from_numpy(a).to(cuda)
+    with torch.no_grad():
+        boxes, objs, obj_scores, rels, pred_scores = prod(t(nb["imgs"]), nb["im_sizes"], 0, t(nb["gt_boxes"]),
+                                                          t(nb["gt_classes"]), t(nb["gt_rels"]))
+    assert np.array_equal(np.asarray(boxes), g[mode + "_boxes"])
+    assert (np.asarray(objs) == g[mode + "_objs"]).mean() >= 0.95            # an argmax may flip on a near-tie of two logits
+    assert np.abs(np.asarray(obj_scores) - g[mode + "_obj_scores"]).max() < 2e-3
+    want_rels, want_scores = g[mode + "_rels"], g[mode + "_pred_scores"]
+    key = lambda r: r[:, 0] * 1000 + r[:, 1]
+    a, b = np.argsort(key(np.asarray(rels))), np.argsort(key(want_rels))
+    assert np.array_equal(np.asarray(rels)[a], want_rels[b])
+    assert np.abs(np.asarray(pred_scores)[a] - want_scores[b]).max() < 2e-3    # probabilities; logits agree to ~4e-4 relative
