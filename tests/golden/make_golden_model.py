@@ -218,6 +218,28 @@ def main():
     print("sgdet ok:", {k: np.asarray(v).shape for k, v in zip("boxes objs obj_scores rels pred_scores".split(), res)})
     np.savez_compressed(os.path.join(HERE, "reference_model_eval.npz"), **out)
 
+    # ---- the ResNet-101 detector (use_resnet=True, "Deprecated" in the reference but BASELINE config 3): GT-box mode, eval
+    ref_od.resnet101 = lambda pretrained=False: torchvision.models.resnet101(weights=None)
+    torch.manual_seed(0)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        det = ref_od.ObjectDetector(CLASSES, mode="gtbox", use_resnet=True)
+    sd = det.state_dict()
+    rout = {"keys": np.array(list(sd.keys())), "shapes": np.array([";".join(map(str, v.shape)) for v in sd.values()])}
+    det.load_state_dict(synthetic_state([(k, tuple(v.shape), v.dtype) for k, v in sd.items()], seed=5))
+    det.eval()
+    nb = make_inputs(seed=13, boxes=12, rels=5)
+    t = torch.from_numpy
+    with torch.no_grad(), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        r = det(t(nb["imgs"]), nb["im_sizes"], 0, t(nb["gt_boxes"]), t(nb["gt_classes"]), return_fmap=True)
+    rout["fmap_sample"] = r.fmap.numpy()[0, ::64, ::4, ::4].copy()
+    rout["fmap_absmax"] = np.array(float(r.fmap.abs().max()))
+    rout["od_obj_dists"] = r.od_obj_dists.numpy()
+    rout["obj_fmap"] = r.obj_fmap.numpy()
+    print("resnet detector ok:", r.fmap.shape, r.od_obj_dists.shape, "fmap absmax %.3f" % float(r.fmap.abs().max()))
+    np.savez_compressed(os.path.join(HERE, "reference_resnet_detector.npz"), **rout)
+
     # ---- SGCls TRAINING forward (models/train_rels.py:118-141): relation sampling with the numpy RNG, training-mode
     # BatchNorm, teacher-forced decoder, both cross-entropies. Dropout probabilities are set to 0 on both sides.
     out = {}

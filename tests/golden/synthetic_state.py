@@ -33,6 +33,8 @@ def synthetic_state(named, seed=0):
             v = torch.randn(shape, generator=g)
         elif "rnn.weight" in key:                                          # flat highway-LSTM weights
             v = torch.randn(shape, generator=g) * 0.03
+        elif key.endswith(".bn3.weight"):                                  # last BN of a ResNet bottleneck: small, so that
+            v = torch.rand(shape, generator=g) * 0.2 + 0.1                 # 33 residual blocks keep activations O(1)
         elif key.endswith(".weight") and len(shape) == 1:                  # BatchNorm scale
             v = torch.rand(shape, generator=g) + 0.5
         else:                                                              # biases

@@ -121,3 +121,25 @@ def test_oracle_relmodel_sgdet_eval_matches_reference_relmodel():
     err = np.abs(np.asarray(pred_scores)[a] - want_scores[b]).max()
     assert err < 1e-3 * max(1.0, float(np.abs(want_scores).max())), err
     assert (np.asarray(rels) == want_rels).all(1).mean() > 0.95
+
+
+def test_oracle_resnet_detector_matches_reference_detector():
+    """ObjectDetector(use_resnet=True) of the reference (object_detector.py:84-138, torchvision resnet101 conv1..layer3,
+    compress, SELU roi_fmap) in GT-box eval mode, run on the CPU, against the oracle's ResNet branch (row a1')."""
+    from oracle import model as OM
+    from golden.synthetic_state import synthetic_state, CLASSES, make_inputs
+    g = np.load(os.path.join(ROOT, "tests", "golden", "reference_resnet_detector.npz"))
+    orc = OM.ObjectDetector(CLASSES, mode="gtbox", use_resnet=True)
+    sd = orc.state_dict()
+    ref_keys = [str(k) for k in g["keys"]]
+    assert set(sd.keys()) == set(ref_keys), (set(sd) ^ set(ref_keys))
+    orc.load_state_dict(synthetic_state([(k, tuple(sd[k].shape), sd[k].dtype) for k in ref_keys], seed=5))
+    orc.eval()
+    nb = make_inputs(seed=13, boxes=12, rels=5)
+    t = torch.from_numpy
+    with torch.no_grad():
+        r = orc(t(nb["imgs"]), nb["im_sizes"], 0, t(nb["gt_boxes"]), t(nb["gt_classes"]))
+    scale = float(g["fmap_absmax"])
+    assert np.abs(r.fmap.numpy()[0, ::64, ::4, ::4] - g["fmap_sample"]).max() < 1e-4 * scale
+    assert np.abs(r.obj_fmap.numpy() - g["obj_fmap"]).max() < 1e-4 * max(1.0, float(np.abs(g["obj_fmap"]).max()))
+    assert np.abs(r.od_obj_dists.numpy() - g["od_obj_dists"]).max() < 1e-4 * max(1.0, float(np.abs(g["od_obj_dists"]).max()))
