@@ -370,7 +370,7 @@ class ObjectDetector(nn.Module):
         x = f.maxpool(f.relu(f.bn1(f.conv1(x))))
         return f.layer3(f.layer2(f.layer1(x)))
 
-    def forward(self, x, im_sizes, image_offset, gt_boxes=None, gt_classes=None, gt_rels=None):
+    def forward(self, x, im_sizes, image_offset, gt_boxes=None, gt_classes=None, gt_rels=None, train_anchor_inds=None):
         with torch.no_grad():
             fmap = self.feature_map(x)
             rel_labels = obj_labels = None
@@ -380,6 +380,24 @@ class ObjectDetector(nn.Module):
                 if gt_rels is not None and self.training:
                     rel_labels = proposal_assignments_gtbox(rois, gt_boxes, gt_classes, gt_rels, image_offset, self.rng)
                 obj_labels = gt_classes[:, 1]
+            elif self.training and self.mode == 'rpntrain':
+                # detector training (models/train_detector.py; object_detector.py:140-191): proposals with the training
+                # limits, RPN outputs at the sampled anchors, proposal -> GT assignment with the injected RNG
+                rpn_feats = self.rpn_head(fmap)
+                rois = self.rpn_head.roi_proposals(rpn_feats, im_sizes, pre_nms_topn=12000, post_nms_topn=2000)
+                tai = train_anchor_inds.clone()
+                tai[:, 0] -= image_offset
+                picked = rpn_feats[tai[:, 0], tai[:, 1], tai[:, 2], tai[:, 3]]                  # gather_nd, :533-545
+                rpn_scores, rpn_box_deltas = picked[:, :2], picked[:, 2:]
+                r, l, tg = host.proposal_assignments_det(t2n(rois), t2n(gt_boxes), t2n(gt_classes), image_offset, self.rng)
+                rois = torch.from_numpy(r)
+                pool = roi_align(fmap, rois)
+                obj_fmap = run_classifier(self.roi_fmap, pool.view(rois.size(0), -1), self.masks, "roi_fmap.")
+                return Result(od_obj_dists=self.score_fc(obj_fmap),
+                              od_box_deltas=self.bbox_fc(obj_fmap).view(-1, len(self.classes), 4),
+                              od_obj_labels=torch.from_numpy(l), od_box_targets=torch.from_numpy(tg),
+                              od_box_priors=rois[:, 1:], rpn_scores=rpn_scores, rpn_box_deltas=rpn_box_deltas,
+                              rois=rois, fmap=fmap)
             else:
                 rois = self.rpn_head.roi_proposals(self.rpn_head(fmap), im_sizes)
             pool = roi_align(self.compress(fmap) if self.use_resnet else fmap, rois)        # :136-137

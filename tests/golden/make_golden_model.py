@@ -240,6 +240,43 @@ def main():
     print("resnet detector ok:", r.fmap.shape, r.od_obj_dists.shape, "fmap absmax %.3f" % float(r.fmap.abs().max()))
     np.savez_compressed(os.path.join(HERE, "reference_resnet_detector.npz"), **rout)
 
+    # ---- detector TRAINING forward (models/train_detector.py:78-117): RPN outputs at the sampled
+    # anchors, 2000 proposals, proposal -> GT assignment, detection heads. proposal_assignments_det orders its candidates
+    # with torch.sort, whose order among equal keys is implementation-defined: this process runs it STABLE (as the oracle
+    # and the product do), so the numpy RNG picks the same rows on both sides.
+    from oracle import host as OH
+    _sort = torch.sort
+
+    def stable_sort(x, *a, **k):
+        dim = a[0] if a else k.get("dim", -1)
+        desc = a[1] if len(a) > 1 else k.get("descending", False)
+        return _sort(x, dim=dim, descending=desc, stable=True)
+    torch.sort = stable_sort
+    torch.manual_seed(0)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        det = ref_od.ObjectDetector(CLASSES, mode="rpntrain", use_resnet=False)
+    sd = det.state_dict()
+    det.load_state_dict(synthetic_state([(k, tuple(v.shape), v.dtype) for k, v in sd.items()], seed=6))
+    det.train()
+    for mod_ in det.modules():
+        if isinstance(mod_, torch.nn.Dropout):
+            mod_.p = 0.0
+    nb = make_inputs(seed=14, boxes=10, rels=4)
+    _, inds, _, _ = OH.anchor_target_layer(nb["gt_boxes"], (592, 592), rng=np.random.RandomState(2))
+    tai = np.column_stack((np.zeros(inds.shape[0], dtype=np.int64), inds)).astype(np.int64)
+    np.random.seed(31)
+    t = torch.from_numpy
+    with torch.no_grad(), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        r = det(t(nb["imgs"]), nb["im_sizes"], 0, t(nb["gt_boxes"]), t(nb["gt_classes"]), None, None, t(tai))
+    torch.sort = _sort
+    dout = {"train_anchor_inds": tai}
+    for k in ("od_obj_dists", "od_box_deltas", "od_obj_labels", "od_box_targets", "od_box_priors", "rpn_scores", "rpn_box_deltas"):
+        dout[k] = getattr(r, k).detach().numpy()
+    print("detector train ok:", {k: v.shape for k, v in dout.items()}, "fg rois", int((dout["od_obj_labels"] > 0).sum()))
+    np.savez_compressed(os.path.join(HERE, "reference_detector_train.npz"), **dout)
+
     # ---- SGCls TRAINING forward (models/train_rels.py:118-141): relation sampling with the numpy RNG, training-mode
     # BatchNorm, teacher-forced decoder, both cross-entropies. Dropout probabilities are set to 0 on both sides.
     out = {}

@@ -143,3 +143,28 @@ def test_oracle_resnet_detector_matches_reference_detector():
     assert np.abs(r.fmap.numpy()[0, ::64, ::4, ::4] - g["fmap_sample"]).max() < 1e-4 * scale
     assert np.abs(r.obj_fmap.numpy() - g["obj_fmap"]).max() < 1e-4 * max(1.0, float(np.abs(g["obj_fmap"]).max()))
     assert np.abs(r.od_obj_dists.numpy() - g["od_obj_dists"]).max() < 1e-4 * max(1.0, float(np.abs(g["od_obj_dists"]).max()))
+
+
+def test_oracle_detector_training_forward_matches_reference_detector():
+    """ObjectDetector(mode='rpntrain').train() of the reference run on the CPU: RPN
+    scores / deltas at the sampled anchors, 2000 proposals -> proposal_assignments_det (stable candidate order, numpy RNG)
+    -> 256 rois with labels and box targets -> detection heads; the inputs of models/train_detector.py's four losses."""
+    from oracle import model as OM
+    from golden.synthetic_state import synthetic_state, CLASSES, make_inputs
+    g = np.load(os.path.join(ROOT, "tests", "golden", "reference_detector_train.npz"))
+    orc = OM.ObjectDetector(CLASSES, mode="rpntrain")
+    sd = orc.state_dict()
+    orc.load_state_dict(synthetic_state([(k, tuple(v.shape), v.dtype) for k, v in sd.items()], seed=6))
+    orc.train()
+    nb = make_inputs(seed=14, boxes=10, rels=4)
+    n = g["od_obj_labels"].shape[0]
+    orc.masks = {"roi_fmap.2": torch.ones(n, 4096), "roi_fmap.5": torch.ones(n, 4096)}
+    orc.rng = np.random.RandomState(31)
+    t = torch.from_numpy
+    r = orc(t(nb["imgs"]), nb["im_sizes"], 0, t(nb["gt_boxes"]), t(nb["gt_classes"]), None, t(g["train_anchor_inds"]))
+    assert np.array_equal(r.od_obj_labels.numpy(), g["od_obj_labels"]) and int((g["od_obj_labels"] > 0).sum()) > 0
+    assert np.allclose(r.od_box_priors.numpy(), g["od_box_priors"], rtol=0, atol=2e-3)        # pixels
+    assert np.array_equal(r.od_box_targets.numpy(), g["od_box_targets"])
+    for k in ("rpn_scores", "rpn_box_deltas", "od_obj_dists", "od_box_deltas"):
+        got, want = getattr(r, k).detach().numpy(), g[k]
+        assert np.abs(got - want).max() < 1e-4 * max(1.0, float(np.abs(want).max())), (k, np.abs(got - want).max())
