@@ -208,6 +208,14 @@ int mb200_bn_relu_backward_split(const float* g, const unsigned char* argmax, co
 /* dx[R,H,W,C] from dcol [R*H*W, 9C] (adjoint of mb200_im2col3_nhwc_split, transposed == 0). */
 int mb200_col2im3_nhwc(const float* dcol, int R, int H, int W, int C, float* dx, cudaStream_t stream);
 
+/* EXPERIMENTAL (csrc/gemm_mn.cu; not yet run on a B200): the same bf16x3 product for operands whose reduction
+ * dimension is the ROW index — C[M,N] (fp32, pitch ldc) = A^T B with A stored [K, M] (pitch lda) and B stored [K, N]
+ * (pitch ldb), (hi, lo) bf16 pairs, M / N contiguous ("MN-major" UMMA operands): the weight-gradient products
+ * dW = dY^T X of every nn.Linear on the path without the transposed operand copies. lda, ldb % 8 == 0. */
+long long mb200_gemm_mn_workspace_floats(int M, int N, int K);
+int mb200_gemm_bf16x3_mn(const void* Ahi, const void* Alo, long long lda, const void* Bhi, const void* Blo, long long ldb,
+                         int M, int N, int K, float* C, long long ldc, float* workspace, cudaStream_t stream);
+
 /* *acc += sum_i x[i]^2 (double accumulator on the device, caller zeroes it): the global gradient norm of
  * clip_grad_norm (lib/pytorch_misc.py:416-459) as one pass per flat buffer. x 16-byte aligned. */
 int mb200_sumsq_accum(const float* x, long long n, double* acc, cudaStream_t stream);

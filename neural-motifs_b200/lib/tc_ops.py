@@ -110,6 +110,32 @@ def gemm(A, B, bias=None, relu=False, want_f32=True, want_split=False, out=None)
     return C if want_f32 else Cs
 
 
+GEMM_MN = __import__("os").environ.get("MOTIFS_GEMM_MN", "0") == "1"   # experimental csrc/gemm_mn.cu for weight gradients
+
+
+def gemm_mn(At, Bt, out=None):
+    """EXPERIMENTAL. C[M,N] = At^T @ Bt with At a SplitMat of [K, M] (rows = the reduction index) and Bt of [K, N]:
+    the weight-gradient product dW = dY^T X straight from the row-major activations (csrc/gemm_mn.cu)."""
+    assert At.rows == Bt.rows, (At.rows, Bt.rows)
+    K, M, N = At.rows, At.K, Bt.K
+    dev = At.hi.device
+    if out is not None:
+        assert out.dtype == torch.float32 and out.is_contiguous() and out.numel() == M * N
+        C = out
+    else:
+        C = torch.empty(M, N, dtype=torch.float32, device=dev)
+    lib = _c.load()
+    ws_n = lib.mb200_gemm_mn_workspace_floats(M, N, K)
+    ws = torch.empty(ws_n, dtype=torch.float32, device=dev) if ws_n > 0 else None
+    ev0 = _prof_begin()
+    with torch.cuda.device(dev):
+        rc = lib.mb200_gemm_bf16x3_mn(_c.ptr(At.hi), _c.ptr(At.lo), At.Kp, _c.ptr(Bt.hi), _c.ptr(Bt.lo), Bt.Kp, M, N, K,
+                                      _c.ptr(C), N, _c.ptr(ws), _c.cur_stream())
+    _c.check(rc, "mb200_gemm_bf16x3_mn")
+    _prof_end("gemm", 2.0 * M * N * K, ev0)
+    return C
+
+
 # ------------------------------------------------------------------ weight split cache
 _cache = {}
 WEIGHT_EPOCH = 0     # bumped by optimizers that update parameters through raw pointers (lib/fused_optim.py)
@@ -222,7 +248,10 @@ class _LinearTC(Function):
             gx = gemm(split_rows(gy), weight_split_t(weight))                 # [M,N] x [K,N]^T -> [M,K]
         if ctx.needs_input_grad[1]:
             tgt = direct_grad_target(weight)
-            gw = gemm(split_transposed(gy), split_transposed(x.detach()), out=tgt)     # [N,M] x [K,M]^T -> [N,K]
+            if GEMM_MN:     # experimental: no transposed operand copies (csrc/gemm_mn.cu)
+                gw = gemm_mn(split_rows(gy), split_rows(x.detach()), out=tgt)
+            else:
+                gw = gemm(split_transposed(gy), split_transposed(x.detach()), out=tgt) # [N,M] x [K,M]^T -> [N,K]
             if tgt is not None:
                 gw = None
         if ctx.has_bias and ctx.needs_input_grad[2]:

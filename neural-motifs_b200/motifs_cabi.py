@@ -59,6 +59,8 @@ SIGNATURES = {
     "mb200_bn_relu_backward": (c_int, [P, P, P, P, P, c_longlong, c_int, P, P, P, P]),
     "mb200_bn_relu_backward_split": (c_int, [P, P, P, P, P, P, c_longlong, c_longlong, c_int, c_int, c_int, P, P, P, P, P, P, P]),
     "mb200_col2im3_nhwc": (c_int, [P, c_int, c_int, c_int, c_int, P, P]),
+    "mb200_gemm_mn_workspace_floats": (c_longlong, [c_int, c_int, c_int]),
+    "mb200_gemm_bf16x3_mn": (c_int, [P, P, c_longlong, P, P, c_longlong, c_int, c_int, c_int, P, c_longlong, P, P]),
     "mb200_sumsq_accum": (c_int, [P, c_longlong, P, P]),
     "mb200_sgd_momentum_clip": (c_int, [P, P, P, c_longlong, c_float, c_float, c_float, P, c_float, c_int, c_int, P]),
     "mb200_sgemm": (c_int, [c_int, c_int, c_int, c_int, c_int, c_float, P, c_int, P, c_int, c_float, P, c_int, P]),
