@@ -195,6 +195,27 @@ def main():
         for k, v in dict(boxes=boxes, objs=objs, obj_scores=obj_scores, rels=rels, pred_scores=pred_scores).items():
             out["%s_%s" % (mode, k)] = np.asarray(v)
         print(mode, "ok:", {k: np.asarray(v).shape for k, v in zip("boxes objs obj_scores rels pred_scores".split(), res)})
+    # ---- constructor variants: object ordering by confidence / size, tanh + limit_vision relation tail
+    for tag, mode, kw in (("var_conf", "predcls", dict(KW, order="confidence", use_tanh=True, limit_vision=True)),
+                          ("var_size", "sgcls", dict(KW, order="size"))):
+        torch.manual_seed(0)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            m = RelModel(CLASSES, RELS, mode=mode, num_gpus=1, require_overlap_det=True, use_resnet=False,
+                         use_proposals=False, pass_in_obj_feats_to_decoder=False, pass_in_obj_feats_to_edge=False,
+                         rec_dropout=0.1, **kw)
+        sd = m.state_dict()
+        m.load_state_dict(synthetic_state([(k, tuple(v.shape), v.dtype) for k, v in sd.items()], seed=3))
+        m.eval()
+        nb = make_inputs(seed=15, boxes=16, rels=6)
+        t = torch.from_numpy
+        with torch.no_grad(), warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            res = m(t(nb["imgs"]), nb["im_sizes"], 0, t(nb["gt_boxes"]), t(nb["gt_classes"]), t(nb["gt_rels"]))
+        for k, v in zip("boxes objs obj_scores rels pred_scores".split(), res):
+            out["%s_%s" % (tag, k)] = np.asarray(v)
+        print(tag, "ok")
+
     # ---- SGDet eval: RPN head -> proposals -> NMS -> detector -> per-class NMS -> overlapping pairs -> context with the
     # decoder's overlap-aware commitments -> relation tail (detector threshold 0 so that random weights yield detections)
     torch.manual_seed(0)

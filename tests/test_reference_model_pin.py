@@ -168,3 +168,29 @@ def test_oracle_detector_training_forward_matches_reference_detector():
     for k in ("rpn_scores", "rpn_box_deltas", "od_obj_dists", "od_box_deltas"):
         got, want = getattr(r, k).detach().numpy(), g[k]
         assert np.abs(got - want).max() < 1e-4 * max(1.0, float(np.abs(want).max())), (k, np.abs(got - want).max())
+
+
+@pytest.mark.parametrize("tag,mode,extra", [("var_conf", "predcls", dict(order="confidence", use_tanh=True, limit_vision=True)),
+                                            ("var_size", "sgcls", dict(order="size"))])
+def test_oracle_relmodel_constructor_variants_match_reference(tag, mode, extra):
+    """Object ordering by confidence / by box size (rel_model.py:139-161) and the tanh + limit_vision relation tail
+    (:515-522) — constructor arguments of the reference's RelModel other than the script configuration."""
+    from oracle import model as OM
+    from golden.synthetic_state import synthetic_state, CLASSES, RELS, KW, make_inputs
+    g = np.load(os.path.join(ROOT, "tests", "golden", "reference_model_eval.npz"))
+    orc = OM.RelModel(CLASSES, RELS, mode=mode, **dict(KW, **extra))
+    sd = orc.state_dict()
+    orc.load_state_dict(synthetic_state([(k, tuple(v.shape), v.dtype) for k, v in sd.items()], seed=3))
+    orc.eval()
+    nb = make_inputs(seed=15, boxes=16, rels=6)
+    t = torch.from_numpy
+    with torch.no_grad():
+        boxes, objs, obj_scores, rels, pred_scores = orc(t(nb["imgs"]), nb["im_sizes"], 0, t(nb["gt_boxes"]),
+                                                         t(nb["gt_classes"]), t(nb["gt_rels"]))
+    assert np.array_equal(np.asarray(objs), g[tag + "_objs"])
+    assert np.allclose(np.asarray(obj_scores), g[tag + "_obj_scores"], rtol=1e-4, atol=1e-6)
+    want_rels, want_scores = g[tag + "_rels"], g[tag + "_pred_scores"]
+    key = lambda r: r[:, 0] * 1000 + r[:, 1]
+    a, b = np.argsort(key(np.asarray(rels))), np.argsort(key(want_rels))
+    assert np.array_equal(np.asarray(rels)[a], want_rels[b])
+    assert np.abs(np.asarray(pred_scores)[a] - want_scores[b]).max() < 1e-4
