@@ -194,9 +194,15 @@ def center_size(b):
 
 
 class LinearizedContext(nn.Module):
-    def __init__(self, classes, rel_classes, mode, embed_dim, hidden_dim, obj_dim, nl_obj, nl_edge, order):
+    def __init__(self, classes, rel_classes, mode, embed_dim, hidden_dim, obj_dim, nl_obj, nl_edge, order,
+                 pass_in_obj_feats_to_decoder=False, pass_in_obj_feats_to_edge=False):
         super().__init__()
         self.classes, self.rel_classes, self.mode, self.order = classes, rel_classes, mode, order
+        # rel_model.py:115-117 sizes the decoder input as hidden + obj_dim + embed_dim while :213 feeds it
+        # obj_dim + embed_dim + 128 + hidden: with pass_in_obj_feats_to_decoder the reference only runs in predcls
+        # (no decoder call); the scripts never set the flag. Restated for predcls only.
+        assert not pass_in_obj_feats_to_decoder or mode == 'predcls', "the reference itself fails on this combination"
+        self.to_decoder, self.to_edge = pass_in_obj_feats_to_decoder, pass_in_obj_feats_to_edge
         self.nl_obj, self.nl_edge = nl_obj, nl_edge
         nc = len(classes)
         self.obj_embed = nn.Embedding(nc, embed_dim)
@@ -205,8 +211,9 @@ class LinearizedContext(nn.Module):
                                        nn.ReLU(inplace=True), nn.Dropout(0.1))
         assert nl_obj > 0 and nl_edge > 0, "oracle restates the MotifNet configuration (nl_obj, nl_edge > 0)"
         self.obj_ctx_rnn = AlternatingHighwayLSTM(obj_dim + embed_dim + 128, hidden_dim, nl_obj)
-        self.decoder_rnn = DecoderRNN(classes, hidden_dim, hidden_dim)
-        self.edge_ctx_rnn = AlternatingHighwayLSTM(embed_dim + hidden_dim, hidden_dim, nl_edge)
+        self.decoder_rnn = DecoderRNN(classes, hidden_dim + (obj_dim + embed_dim if self.to_decoder else 0), hidden_dim)
+        self.edge_ctx_rnn = AlternatingHighwayLSTM(embed_dim + hidden_dim + (obj_dim if self.to_edge else 0), hidden_dim,
+                                                   nl_edge)
         self.masks = None
 
     def sort_rois(self, batch_idx, confidence, box_priors):
@@ -247,7 +254,8 @@ class LinearizedContext(nn.Module):
             obj_dists2[torch.arange(obj_labels.size(0)), obj_labels] = 1000.0
         obj_ctx = enc[inv]
         # edge_ctx (:171-195)
-        inp_feats = torch.cat((self.obj_embed2(obj_preds), obj_ctx), 1)
+        edge_in = torch.cat((obj_fmaps, obj_ctx), 1) if self.to_edge else obj_ctx            # :287
+        inp_feats = torch.cat((self.obj_embed2(obj_preds), edge_in), 1)
         conf = F.softmax(obj_dists2.detach(), 1).view(-1)[obj_preds + torch.arange(obj_preds.size(0)) * nc]
         perm, inv, ls = self.sort_rois(im_inds, conf, box_priors)
         edge = self.edge_ctx_rnn(inp_feats[perm], ls, m.get("edge_ctx_rnn"))[inv]
@@ -479,16 +487,20 @@ class Flattener(nn.Module):
 class RelModel(nn.Module):
     def __init__(self, classes, rel_classes, mode='sgcls', embed_dim=200, hidden_dim=512, pooling_dim=4096,
                  nl_obj=2, nl_edge=4, order='leftright', thresh=0.01, use_bias=True, use_tanh=False,
-                 limit_vision=False, require_overlap_det=True):
+                 limit_vision=False, require_overlap_det=True, pass_in_obj_feats_to_decoder=False,
+                 pass_in_obj_feats_to_edge=False):
         super().__init__()
         self.classes, self.rel_classes, self.mode = classes, rel_classes, mode
         self.pooling_dim, self.use_bias, self.use_tanh, self.limit_vision = pooling_dim, use_bias, use_tanh, limit_vision
         self.require_overlap = require_overlap_det and mode == 'sgdet'
         self.detector = ObjectDetector(classes, mode='refinerels' if mode == 'sgdet' else 'gtbox', thresh=thresh)
-        self.context = LinearizedContext(classes, rel_classes, mode, embed_dim, hidden_dim, 4096, nl_obj, nl_edge, order)
+        self.context = LinearizedContext(classes, rel_classes, mode, embed_dim, hidden_dim, 4096, nl_obj, nl_edge, order,
+                                         pass_in_obj_feats_to_decoder, pass_in_obj_feats_to_edge)
         self.union_boxes = UnionBoxesAndFeats(7, 16, 512)
-        self.roi_fmap = nn.Sequential(Flattener(), load_vgg(use_dropout=False, use_relu=False,
-                                                            use_linear=pooling_dim == 4096).classifier)
+        roi_fmap = [Flattener(), load_vgg(use_dropout=False, use_relu=False, use_linear=pooling_dim == 4096).classifier]
+        if pooling_dim != 4096:                                 # rel_model.py:371-372
+            roi_fmap.append(nn.Linear(4096, pooling_dim))
+        self.roi_fmap = nn.Sequential(*roi_fmap)
         self.roi_fmap_obj = load_vgg().classifier
         self.post_lstm = nn.Linear(hidden_dim, pooling_dim * 2)
         self.rel_compress = nn.Linear(pooling_dim, len(rel_classes), bias=True)
@@ -519,6 +531,8 @@ class RelModel(nn.Module):
         prod_rep = edge_rep[:, 0][rel_inds[:, 1]] * edge_rep[:, 1][rel_inds[:, 2]]
         ub = self.union_boxes(result.fmap, rois, rel_inds[:, 1:])
         vr = run_classifier(self.roi_fmap[1], ub.view(ub.size(0), -1), self.masks, "roi_fmap.1.")
+        if len(self.roi_fmap) > 2:                              # pooling_dim != 4096: the extra projection, rel_model.py:371-372
+            vr = self.roi_fmap[2](vr)
         if self.limit_vision:
             prod_rep = torch.cat((prod_rep[:, :2048] * vr[:, :2048], prod_rep[:, 2048:]), 1)
         else:

@@ -216,6 +216,26 @@ def main():
             out["%s_%s" % (tag, k)] = np.asarray(v)
         print(tag, "ok")
 
+    # ---- the reference's DEFAULT constructor arguments (rel_model.py:303-308: hidden 256, pooling 2048, nl_obj 1, nl_edge 2,
+    # order confidence, pass_in_obj_feats_to_decoder / _to_edge True, tanh, limit_vision), PredCls
+    torch.manual_seed(0)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        m = RelModel(CLASSES, RELS, mode="predcls")
+    sd = m.state_dict()
+    out["var_default_keys"] = np.array(list(sd.keys()))
+    out["var_default_shapes"] = np.array([";".join(map(str, v.shape)) for v in sd.values()])
+    m.load_state_dict(synthetic_state([(k, tuple(v.shape), v.dtype) for k, v in sd.items()], seed=3))
+    m.eval()
+    nb = make_inputs(seed=16, boxes=11, rels=5)
+    t = torch.from_numpy
+    with torch.no_grad(), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        res = m(t(nb["imgs"]), nb["im_sizes"], 0, t(nb["gt_boxes"]), t(nb["gt_classes"]), t(nb["gt_rels"]))
+    for k, v in zip("boxes objs obj_scores rels pred_scores".split(), res):
+        out["var_default_" + k] = np.asarray(v)
+    print("var_default ok")
+
     # ---- SGDet eval: RPN head -> proposals -> NMS -> detector -> per-class NMS -> overlapping pairs -> context with the
     # decoder's overlap-aware commitments -> relation tail (detector threshold 0 so that random weights yield detections)
     torch.manual_seed(0)

@@ -194,3 +194,32 @@ def test_oracle_relmodel_constructor_variants_match_reference(tag, mode, extra):
     a, b = np.argsort(key(np.asarray(rels))), np.argsort(key(want_rels))
     assert np.array_equal(np.asarray(rels)[a], want_rels[b])
     assert np.abs(np.asarray(pred_scores)[a] - want_scores[b]).max() < 1e-4
+
+
+def test_oracle_relmodel_reference_default_arguments_predcls():
+    """`RelModel(classes, rel_classes, mode='predcls')` with the reference's DEFAULT constructor arguments
+    (rel_model.py:303-308): hidden 256, pooling 2048 (fc7 dropped from the union branch, limit_vision slicing), nl_obj 1,
+    nl_edge 2, ordering by confidence, object features passed to the edge LSTM, tanh."""
+    from oracle import model as OM
+    from golden.synthetic_state import synthetic_state, CLASSES, RELS, make_inputs
+    g = np.load(os.path.join(ROOT, "tests", "golden", "reference_model_eval.npz"))
+    orc = OM.RelModel(CLASSES, RELS, mode="predcls", embed_dim=200, hidden_dim=256, pooling_dim=2048, nl_obj=1, nl_edge=2,
+                      order="confidence", thresh=0.01, use_bias=True, use_tanh=True, limit_vision=True,
+                      pass_in_obj_feats_to_decoder=True, pass_in_obj_feats_to_edge=True)
+    sd = orc.state_dict()
+    ref_keys = [str(k) for k in g["var_default_keys"]]
+    ref_shapes = {k: tuple(int(v) for v in s.split(";") if v) for k, s in zip(ref_keys, g["var_default_shapes"])}
+    assert set(sd.keys()) == set(ref_keys), (set(sd) ^ set(ref_keys))
+    assert all(tuple(sd[k].shape) == ref_shapes[k] for k in ref_keys), [k for k in ref_keys if tuple(sd[k].shape) != ref_shapes[k]]
+    orc.load_state_dict(synthetic_state([(k, ref_shapes[k], sd[k].dtype) for k in ref_keys], seed=3))
+    orc.eval()
+    nb = make_inputs(seed=16, boxes=11, rels=5)
+    t = torch.from_numpy
+    with torch.no_grad():
+        boxes, objs, obj_scores, rels, pred_scores = orc(t(nb["imgs"]), nb["im_sizes"], 0, t(nb["gt_boxes"]),
+                                                         t(nb["gt_classes"]), t(nb["gt_rels"]))
+    want_rels, want_scores = g["var_default_rels"], g["var_default_pred_scores"]
+    key = lambda r: r[:, 0] * 1000 + r[:, 1]
+    a, b = np.argsort(key(np.asarray(rels))), np.argsort(key(want_rels))
+    assert np.array_equal(np.asarray(rels)[a], want_rels[b])
+    assert np.abs(np.asarray(pred_scores)[a] - want_scores[b]).max() < 1e-4
