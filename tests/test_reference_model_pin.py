@@ -18,19 +18,49 @@ sys.path.insert(0, os.path.join(ROOT, "neural-motifs_b200"))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 
+_CACHE = {}
+
+
+def script_config_oracle(mode, **attrs):
+    """ONE oracle RelModel in the script configuration serves every test of this file that uses it: the state dict does
+    not depend on the mode / ordering / tail flags, which are plain attributes (building the three VGG fc stacks and
+    regenerating 1.7 GB of synthetic weights per test would triple the run time of the CPU suite)."""
+    from oracle import model as OM
+    from golden.synthetic_state import synthetic_state, CLASSES, RELS, KW
+    if "orc" not in _CACHE:
+        orc = OM.RelModel(CLASSES, RELS, mode="sgcls", **KW)
+        sd = orc.state_dict()
+        _CACHE["state"] = synthetic_state([(k, tuple(v.shape), v.dtype) for k, v in sd.items()], seed=3)
+        _CACHE["orc"] = orc
+    orc = _CACHE["orc"]
+    orc.load_state_dict(_CACHE["state"])                       # a training-mode test may have moved the BatchNorm buffers
+    orc.mode = orc.context.mode = mode
+    orc.detector.mode = 'refinerels' if mode == 'sgdet' else 'gtbox'
+    orc.require_overlap = mode == 'sgdet'
+    orc.detector.thresh = attrs.pop("thresh", 0.01)
+    orc.context.order = attrs.pop("order", KW["order"])
+    orc.use_tanh = attrs.pop("use_tanh", KW["use_tanh"])
+    orc.limit_vision = attrs.pop("limit_vision", KW["limit_vision"])
+    assert not attrs, attrs
+    for p_ in orc.parameters():
+        p_.requires_grad = True
+        p_.grad = None
+    orc.masks = orc.detector.masks = orc.context.masks = None
+    return orc
+
+
 @pytest.mark.parametrize("mode", ["predcls", "sgcls"])
 def test_oracle_relmodel_eval_matches_reference_relmodel(mode):
     from oracle import model as OM
     from golden.synthetic_state import synthetic_state, CLASSES, RELS, KW, make_inputs
     g = np.load(os.path.join(ROOT, "tests", "golden", "reference_model_eval.npz"))
-    orc = OM.RelModel(CLASSES, RELS, mode=mode, **KW)
+    orc = script_config_oracle(mode)
     sd = orc.state_dict()
     ref_keys = [str(k) for k in g[mode + "_keys"]]
     ref_shapes = {k: tuple(int(v) for v in s.split(";") if v) for k, s in zip(ref_keys, g[mode + "_shapes"])}
     # the reference's state dict and the oracle's (= the product's) are interchangeable: same keys, same shapes
     assert set(sd.keys()) == set(ref_keys), (set(sd) ^ set(ref_keys))
     assert all(tuple(sd[k].shape) == ref_shapes[k] for k in ref_keys)
-    orc.load_state_dict(synthetic_state([(k, ref_shapes[k], sd[k].dtype) for k in ref_keys], seed=3))
     orc.eval()
     nb = make_inputs(seed=11)
     t = torch.from_numpy
@@ -60,9 +90,7 @@ def test_oracle_relmodel_sgcls_train_forward_matches_reference_relmodel():
     from golden.synthetic_state import synthetic_state, CLASSES, RELS, KW, make_inputs
     from model_utils import make_masks
     g = np.load(os.path.join(ROOT, "tests", "golden", "reference_model_train.npz"))
-    orc = OM.RelModel(CLASSES, RELS, mode="sgcls", **KW)
-    sd = orc.state_dict()
-    orc.load_state_dict(synthetic_state([(k, tuple(v.shape), v.dtype) for k, v in sd.items()], seed=3))
+    orc = script_config_oracle("sgcls")
     orc.train()
     nb = make_inputs(seed=12, boxes=14, rels=9)
     n_obj, n_rel = 14, g["train_rel_labels"].shape[0]
@@ -100,11 +128,9 @@ def test_oracle_relmodel_sgdet_eval_matches_reference_relmodel():
     from oracle import model as OM
     from golden.synthetic_state import synthetic_state, CLASSES, RELS, KW, make_inputs
     g = np.load(os.path.join(ROOT, "tests", "golden", "reference_model_eval.npz"))
-    orc = OM.RelModel(CLASSES, RELS, mode="sgdet", thresh=0.0, **KW)
-    sd = orc.state_dict()
+    orc = script_config_oracle("sgdet", thresh=0.0)
     ref_keys = [str(k) for k in g["sgdet_keys"]]
-    assert set(sd.keys()) == set(ref_keys), (set(sd) ^ set(ref_keys))
-    orc.load_state_dict(synthetic_state([(k, tuple(sd[k].shape), sd[k].dtype) for k in ref_keys], seed=3))
+    assert set(orc.state_dict().keys()) == set(ref_keys)
     orc.eval()
     nb = make_inputs(seed=11)
     with torch.no_grad():
@@ -178,9 +204,7 @@ def test_oracle_relmodel_constructor_variants_match_reference(tag, mode, extra):
     from oracle import model as OM
     from golden.synthetic_state import synthetic_state, CLASSES, RELS, KW, make_inputs
     g = np.load(os.path.join(ROOT, "tests", "golden", "reference_model_eval.npz"))
-    orc = OM.RelModel(CLASSES, RELS, mode=mode, **dict(KW, **extra))
-    sd = orc.state_dict()
-    orc.load_state_dict(synthetic_state([(k, tuple(v.shape), v.dtype) for k, v in sd.items()], seed=3))
+    orc = script_config_oracle(mode, **extra)
     orc.eval()
     nb = make_inputs(seed=15, boxes=16, rels=6)
     t = torch.from_numpy
