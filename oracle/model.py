@@ -433,7 +433,14 @@ class ObjectDetector(nn.Module):
                 return None
             nms_inds, nms_scores, nms_labels = [torch.cat(z, 0) for z in zip(*dets)]
             nms_boxes = torch.cat((rois[:, 1:][nms_inds][:, None], boxes[nms_inds][:, 1:]), 1)
-            return Result(rm_obj_dists=od_obj_dists[nms_inds], rm_obj_labels=None, rm_box_priors=nms_boxes[:, 0],
+            rm_obj_labels = None
+            if self.training:           # SGDet training (:316-326): label the detections by IoU >= 0.5 with a GT box of the image
+                ov = torch.from_numpy(ops.bbox_overlaps_f32(t2n(nms_boxes[:, 0]), t2n(gt_boxes)))
+                ov[(inds[nms_inds] + image_offset)[:, None] != gt_classes[None, :, 0]] = 0.0
+                mx, am = ov.max(1)
+                rm_obj_labels = gt_classes[:, 1][am].clone()
+                rm_obj_labels[mx < 0.5] = 0
+            return Result(rm_obj_dists=od_obj_dists[nms_inds], rm_obj_labels=rm_obj_labels, rm_box_priors=nms_boxes[:, 0],
                           boxes_all=nms_boxes, rel_labels=None, im_inds=inds[nms_inds] + image_offset, fmap=fmap,
                           od_obj_dists=od_obj_dists, obj_fmap=obj_fmap[nms_inds], rois=rois, obj_scores=nms_scores,
                           obj_preds=nms_labels)
@@ -512,6 +519,12 @@ class RelModel(nn.Module):
         result = self.detector(x, im_sizes, image_offset, gt_boxes, gt_classes, gt_rels)
         im_inds = result.im_inds - image_offset
         boxes = result.rm_box_priors
+        if self.training and result.rel_labels is None:
+            # SGDet training (rel_model.py:479-487): relation labels for the DETECTED boxes
+            assert self.mode == 'sgdet'
+            result.rel_labels = torch.from_numpy(host.rel_assignments(
+                t2n(im_inds), t2n(boxes), t2n(result.rm_obj_labels), t2n(gt_boxes), t2n(gt_classes), t2n(gt_rels),
+                image_offset, self.detector.rng, filter_non_overlap=True, num_sample_per_gt=1))
         if self.training:
             rel_inds = result.rel_labels[:, :3].clone()
         else:

@@ -358,6 +358,56 @@ def main():
     out["train_bn_running_mean"] = m.union_boxes.conv[2].running_mean.numpy().copy()
     print("sgcls train ok: loss %.5f, rel_labels %s (%d fg)" % (float(loss), tuple(res.rel_labels.shape),
                                                                  int((res.rel_labels[:, -1] > 0).sum())))
+    # ---- SGDet TRAINING forward (scripts/refine_for_detection.sh): detections from the frozen detector, IoU relabelling,
+    # rel_assignments on the detected boxes (numpy RNG), decoder teacher-forced with background labels, both losses
+    torch.manual_seed(0)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        m = RelModel(CLASSES, RELS, mode="sgdet", num_gpus=1, require_overlap_det=True, use_resnet=False,
+                     use_proposals=False, pass_in_obj_feats_to_decoder=False, pass_in_obj_feats_to_edge=False,
+                     rec_dropout=0.0, thresh=0.0, **KW)
+    sd = m.state_dict()
+    m.load_state_dict(synthetic_state([(k, tuple(v.shape), v.dtype) for k, v in sd.items()], seed=3))
+    m.train()
+    for p_ in m.detector.parameters():
+        p_.requires_grad = False
+    for mod_ in m.modules():
+        if isinstance(mod_, (torch.nn.Dropout, torch.nn.AlphaDropout)):
+            mod_.p = 0.0
+    nb = make_inputs(seed=11)
+    from oracle import host as OH2
+    _, inds, _, _ = OH2.anchor_target_layer(nb["gt_boxes"], (592, 592), rng=np.random.RandomState(2))
+    tai = np.column_stack((np.zeros(inds.shape[0], dtype=np.int64), inds)).astype(np.int64)
+    # With random weights no detection overlaps the random GT boxes. The detections do not depend on the GT (RPN path), so a
+    # first pass collects them and the GT of the fixture is built FROM them: 10 detections (jittered) become the GT boxes.
+    seen = {}
+    hk = m.detector.register_forward_hook(lambda mod, inp, outp: seen.__setitem__("res", outp))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        np.random.seed(40)
+        m(t(nb["imgs"]), nb["im_sizes"], 0, t(nb["gt_boxes"]), t(nb["gt_classes"]), t(nb["gt_rels"]), None, t(tai))
+    hk.remove()
+    priors = seen["res"].rm_box_priors.detach().numpy()
+    rng = np.random.RandomState(5)
+    pick = np.arange(0, priors.shape[0], max(1, priors.shape[0] // 10))[:10]
+    gt_boxes2 = np.clip(priors[pick] + rng.uniform(-2, 2, (len(pick), 4)), 0, 591).astype(np.float32)
+    gt_classes2 = np.stack([np.zeros(len(pick)), rng.randint(1, 151, len(pick))], 1).astype(np.int64)
+    pairs = [(a, b) for a in range(len(pick)) for b in range(len(pick)) if a != b]
+    sel = np.sort(rng.choice(len(pairs), 12, replace=False))
+    gt_rels2 = np.array([[0, pairs[k][0], pairs[k][1], rng.randint(1, 51)] for k in sel], dtype=np.int64)
+    out["sgdet_train_gt_boxes"], out["sgdet_train_gt_classes"], out["sgdet_train_gt_rels"] = gt_boxes2, gt_classes2, gt_rels2
+    np.random.seed(41)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        res = m(t(nb["imgs"]), nb["im_sizes"], 0, t(gt_boxes2), t(gt_classes2), t(gt_rels2), None, t(tai))
+    loss = F.cross_entropy(res.rm_obj_dists, res.rm_obj_labels) + F.cross_entropy(res.rel_dists, res.rel_labels[:, -1])
+    for k in ("rm_obj_dists", "rm_obj_labels", "rel_dists", "rel_labels"):
+        out["sgdet_train_" + k] = getattr(res, k).detach().numpy()
+    out["sgdet_train_loss"] = np.array(float(loss.detach()))
+    out["sgdet_train_anchor_inds"] = tai
+    print("sgdet train ok: loss %.5f, %d detections (%d labelled), rel_labels %s (%d fg)" % (
+        float(loss.detach()), res.rm_obj_labels.size(0), int((res.rm_obj_labels > 0).sum()), tuple(res.rel_labels.shape),
+        int((res.rel_labels[:, -1] > 0).sum())))
     np.savez_compressed(os.path.join(HERE, "reference_model_train.npz"), **out)
     return RelModel
 

@@ -247,3 +247,33 @@ def test_oracle_relmodel_reference_default_arguments_predcls():
     a, b = np.argsort(key(np.asarray(rels))), np.argsort(key(want_rels))
     assert np.array_equal(np.asarray(rels)[a], want_rels[b])
     assert np.abs(np.asarray(pred_scores)[a] - want_scores[b]).max() < 1e-4
+
+
+def test_oracle_relmodel_sgdet_train_forward_matches_reference_relmodel():
+    """SGDet TRAINING forward (scripts/refine_for_detection.sh): RPN proposals -> per-class NMS detections -> IoU
+    relabelling against the GT boxes -> rel_assignments on the detected boxes (numpy RNG) -> context with the decoder
+    teacher-forced on labels that contain background -> both cross-entropies. The fixture's GT boxes are built from the
+    model's own detections so that labelled detections and foreground relations exist."""
+    import torch.nn.functional as F
+    from golden.synthetic_state import make_inputs
+    from model_utils import make_masks
+    g = np.load(os.path.join(ROOT, "tests", "golden", "reference_model_train.npz"))
+    orc = script_config_oracle("sgdet", thresh=0.0)
+    orc.train()
+    nb = make_inputs(seed=11)
+    n_det, n_rel = g["sgdet_train_rm_obj_labels"].shape[0], g["sgdet_train_rel_labels"].shape[0]
+    det, top, ctx = make_masks(n_det, n_rel, 1, seed=0)
+    ones = lambda d: {k: torch.ones_like(v) for k, v in d.items()}
+    orc.masks, orc.context.masks = ones(top), ones(ctx)
+    orc.detector.masks = {"roi_fmap.2": torch.ones(1, 4096), "roi_fmap.5": torch.ones(1, 4096)}      # broadcast over the rois
+    orc.detector.rng = np.random.RandomState(41)
+    t = torch.from_numpy
+    res = orc(t(nb["imgs"]), nb["im_sizes"], 0, t(g["sgdet_train_gt_boxes"]), t(g["sgdet_train_gt_classes"]),
+              t(g["sgdet_train_gt_rels"]))
+    assert np.array_equal(res.rm_obj_labels.numpy(), g["sgdet_train_rm_obj_labels"]) and int((res.rm_obj_labels > 0).sum()) > 5
+    assert np.array_equal(res.rel_labels.numpy(), g["sgdet_train_rel_labels"]) and int((res.rel_labels[:, -1] > 0).sum()) > 0
+    for k, tol in (("rm_obj_dists", 1e-3), ("rel_dists", 1e-3)):
+        got, want = getattr(res, k).detach().numpy(), g["sgdet_train_" + k]
+        assert np.abs(got - want).max() < tol * max(1.0, float(np.abs(want).max())), (k, np.abs(got - want).max())
+    loss = F.cross_entropy(res.rm_obj_dists, res.rm_obj_labels) + F.cross_entropy(res.rel_dists, res.rel_labels[:, -1])
+    assert abs(float(loss.detach()) - float(g["sgdet_train_loss"])) < 1e-3 * float(g["sgdet_train_loss"])
