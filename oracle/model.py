@@ -209,11 +209,14 @@ class LinearizedContext(nn.Module):
         self.obj_embed2 = nn.Embedding(nc, embed_dim)
         self.pos_embed = nn.Sequential(nn.BatchNorm1d(4, momentum=BATCHNORM_MOMENTUM / 10.0), nn.Linear(4, 128),
                                        nn.ReLU(inplace=True), nn.Dropout(0.1))
-        assert nl_obj > 0 and nl_edge > 0, "oracle restates the MotifNet configuration (nl_obj, nl_edge > 0)"
-        self.obj_ctx_rnn = AlternatingHighwayLSTM(obj_dim + embed_dim + 128, hidden_dim, nl_obj)
-        self.decoder_rnn = DecoderRNN(classes, hidden_dim + (obj_dim + embed_dim if self.to_decoder else 0), hidden_dim)
-        self.edge_ctx_rnn = AlternatingHighwayLSTM(embed_dim + hidden_dim + (obj_dim if self.to_edge else 0), hidden_dim,
-                                                   nl_edge)
+        if nl_obj > 0:
+            self.obj_ctx_rnn = AlternatingHighwayLSTM(obj_dim + embed_dim + 128, hidden_dim, nl_obj)
+            self.decoder_rnn = DecoderRNN(classes, hidden_dim + (obj_dim + embed_dim if self.to_decoder else 0), hidden_dim)
+        else:                           # the scripts' "baseline" (-nl_obj 0 -nl_edge 0): a linear object classifier, :125-126
+            self.decoder_lin = nn.Linear(obj_dim + embed_dim + 128, nc)
+        if nl_edge > 0:                 # :128-137
+            self.edge_ctx_rnn = AlternatingHighwayLSTM(embed_dim + (hidden_dim if nl_obj > 0 else 0)
+                                                       + (obj_dim if self.to_edge else 0), hidden_dim, nl_edge)
         self.masks = None
 
     def sort_rois(self, batch_idx, confidence, box_priors):
@@ -238,21 +241,42 @@ class LinearizedContext(nn.Module):
         if self.training:
             pos = pos * m["pos_embed.3"]
         obj_pre_rep = torch.cat((obj_fmaps, obj_embed, pos), 1)
-        # obj_ctx (:197-234)
-        confidence = F.softmax(obj_logits, 1).detach()[:, 1:].max(1)[0]
-        perm, inv, ls = self.sort_rois(im_inds, confidence, box_priors)
-        inp = obj_pre_rep[perm].contiguous()
-        enc = self.obj_ctx_rnn(inp, ls, m.get("obj_ctx_rnn"))
-        if self.mode != 'predcls':
-            d, p = self.decoder_rnn(enc, ls, labels=obj_labels[perm] if obj_labels is not None else None,
-                                    boxes_for_nms=boxes_per_cls[perm] if boxes_per_cls is not None else None,
-                                    dropout_mask=m.get("decoder_rnn"))
-            obj_preds, obj_dists2 = p[inv], d[inv]
+        if self.nl_obj > 0:
+            # obj_ctx (:197-234)
+            confidence = F.softmax(obj_logits, 1).detach()[:, 1:].max(1)[0]
+            perm, inv, ls = self.sort_rois(im_inds, confidence, box_priors)
+            inp = obj_pre_rep[perm].contiguous()
+            enc = self.obj_ctx_rnn(inp, ls, m.get("obj_ctx_rnn"))
+            if self.mode != 'predcls':
+                d, p = self.decoder_rnn(enc, ls, labels=obj_labels[perm] if obj_labels is not None else None,
+                                        boxes_for_nms=boxes_per_cls[perm] if boxes_per_cls is not None else None,
+                                        dropout_mask=m.get("decoder_rnn"))
+                obj_preds, obj_dists2 = p[inv], d[inv]
+            else:
+                obj_preds = obj_labels
+                obj_dists2 = torch.full((obj_labels.size(0), nc), -1000.0)
+                obj_dists2[torch.arange(obj_labels.size(0)), obj_labels] = 1000.0
+            obj_ctx = enc[inv]
         else:
-            obj_preds = obj_labels
-            obj_dists2 = torch.full((obj_labels.size(0), nc), -1000.0)
-            obj_dists2[torch.arange(obj_labels.size(0)), obj_labels] = 1000.0
-        obj_ctx = enc[inv]
+            # no object context (:259-283): linear classifier; SGDet eval picks labels through a per-class NMS
+            if self.mode == 'predcls':
+                obj_dists2 = torch.full((obj_labels.size(0), nc), -1000.0)
+                obj_dists2[torch.arange(obj_labels.size(0)), obj_labels] = 1000.0
+            else:
+                obj_dists2 = self.decoder_lin(obj_pre_rep)
+            if self.mode == 'sgdet' and not self.training:
+                probs = F.softmax(obj_dists2, 1)
+                nms_mask = torch.zeros_like(probs)
+                for c in range(1, nc):
+                    keep = ops.apply_nms(t2n(probs[:, c]), t2n(boxes_per_cls[:, c]), pre_nms_topn=probs.size(0),
+                                         post_nms_topn=probs.size(0), nms_thresh=0.3)
+                    nms_mask[:, c][torch.from_numpy(np.asarray(keep, dtype=np.int64))] = 1
+                obj_preds = (nms_mask * probs)[:, 1:].max(1)[1] + 1
+            else:
+                obj_preds = obj_labels if obj_labels is not None else obj_dists2[:, 1:].max(1)[1] + 1
+            obj_ctx = obj_pre_rep
+        if self.nl_edge == 0:
+            return obj_dists2, obj_preds, None
         # edge_ctx (:171-195)
         edge_in = torch.cat((obj_fmaps, obj_ctx), 1) if self.to_edge else obj_ctx            # :287
         inp_feats = torch.cat((self.obj_embed2(obj_preds), edge_in), 1)
@@ -510,6 +534,8 @@ class RelModel(nn.Module):
         self.roi_fmap = nn.Sequential(*roi_fmap)
         self.roi_fmap_obj = load_vgg().classifier
         self.post_lstm = nn.Linear(hidden_dim, pooling_dim * 2)
+        if nl_edge == 0:                                        # rel_model.py:386-388
+            self.post_emb = nn.Embedding(len(classes), pooling_dim * 2)
         self.rel_compress = nn.Linear(pooling_dim, len(rel_classes), bias=True)
         if use_bias:
             self.freq_bias = FrequencyBias(len(classes), len(rel_classes))
@@ -540,7 +566,7 @@ class RelModel(nn.Module):
         result.rm_obj_dists, result.obj_preds, edge_ctx = self.context(
             result.obj_fmap, result.rm_obj_dists.detach(), im_inds,
             result.rm_obj_labels if self.training or self.mode == 'predcls' else None, boxes.detach(), result.boxes_all)
-        edge_rep = self.post_lstm(edge_ctx).view(-1, 2, self.pooling_dim)
+        edge_rep = (self.post_emb(result.obj_preds) if edge_ctx is None else self.post_lstm(edge_ctx)).view(-1, 2, self.pooling_dim)
         prod_rep = edge_rep[:, 0][rel_inds[:, 1]] * edge_rep[:, 1][rel_inds[:, 2]]
         ub = self.union_boxes(result.fmap, rois, rel_inds[:, 1:])
         vr = run_classifier(self.roi_fmap[1], ub.view(ub.size(0), -1), self.masks, "roi_fmap.1.")

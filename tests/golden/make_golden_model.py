@@ -236,6 +236,32 @@ def main():
         out["var_default_" + k] = np.asarray(v)
     print("var_default ok")
 
+    # ---- the scripts' "baseline" configuration (train_models_sgcls.sh:8, eval_models_sg*.sh: -nl_obj 0 -nl_edge 0): linear
+    # object classifier instead of the context LSTMs, post_emb instead of post_lstm; SGCls and SGDet (per-class NMS labels)
+    KW0 = dict(KW, nl_obj=0, nl_edge=0)
+    for tag, mode, th in (("base_sgcls", "sgcls", 0.01), ("base_sgdet", "sgdet", 0.0)):
+        torch.manual_seed(0)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            m = RelModel(CLASSES, RELS, mode=mode, num_gpus=1, require_overlap_det=True, use_resnet=False,
+                         use_proposals=False, pass_in_obj_feats_to_decoder=False, pass_in_obj_feats_to_edge=False,
+                         rec_dropout=0.1, thresh=th, **KW0)
+        sd = m.state_dict()
+        out[tag + "_keys"] = np.array(list(sd.keys()))
+        m.load_state_dict(synthetic_state([(k, tuple(v.shape), v.dtype) for k, v in sd.items()], seed=3))
+        m.eval()
+        nb = make_inputs(seed=17, boxes=13, rels=5)
+        t = torch.from_numpy
+        with torch.no_grad(), warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            if mode == "sgdet":
+                res = m(t(nb["imgs"]), nb["im_sizes"], 0)
+            else:
+                res = m(t(nb["imgs"]), nb["im_sizes"], 0, t(nb["gt_boxes"]), t(nb["gt_classes"]), t(nb["gt_rels"]))
+        for k, v in zip("boxes objs obj_scores rels pred_scores".split(), res):
+            out["%s_%s" % (tag, k)] = np.asarray(v)
+        print(tag, "ok", np.asarray(res[3]).shape)
+
     # ---- SGDet eval: RPN head -> proposals -> NMS -> detector -> per-class NMS -> overlapping pairs -> context with the
     # decoder's overlap-aware commitments -> relation tail (detector threshold 0 so that random weights yield detections)
     torch.manual_seed(0)

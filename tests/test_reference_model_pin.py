@@ -277,3 +277,41 @@ def test_oracle_relmodel_sgdet_train_forward_matches_reference_relmodel():
         assert np.abs(got - want).max() < tol * max(1.0, float(np.abs(want).max())), (k, np.abs(got - want).max())
     loss = F.cross_entropy(res.rm_obj_dists, res.rm_obj_labels) + F.cross_entropy(res.rel_dists, res.rel_labels[:, -1])
     assert abs(float(loss.detach()) - float(g["sgdet_train_loss"])) < 1e-3 * float(g["sgdet_train_loss"])
+
+
+@pytest.mark.parametrize("tag,mode,thresh", [("base_sgcls", "sgcls", 0.01), ("base_sgdet", "sgdet", 0.0)])
+def test_oracle_baseline_configuration_matches_reference(tag, mode, thresh):
+    """The scripts' "baseline" (`-nl_obj 0 -nl_edge 0`, scripts/train_models_sgcls.sh:8, eval_models_sg*.sh): linear object
+    classifier instead of the context LSTMs (rel_model.py:125-126, 259-283 incl. the per-class NMS label choice of SGDet
+    eval) and `post_emb` instead of `post_lstm` (:386-388, 500-503)."""
+    from oracle import model as OM
+    from golden.synthetic_state import synthetic_state, CLASSES, RELS, KW, make_inputs
+    g = np.load(os.path.join(ROOT, "tests", "golden", "reference_model_eval.npz"))
+    if "base" not in _CACHE:                                   # one build serves both modes (same state dict)
+        orc = OM.RelModel(CLASSES, RELS, mode="sgcls", **dict(KW, nl_obj=0, nl_edge=0))
+        sd = orc.state_dict()
+        orc.load_state_dict(synthetic_state([(k, tuple(v.shape), v.dtype) for k, v in sd.items()], seed=3))
+        _CACHE["base"] = orc
+    orc = _CACHE["base"]
+    orc.mode = orc.context.mode = mode
+    orc.detector.mode = 'refinerels' if mode == 'sgdet' else 'gtbox'
+    orc.require_overlap = mode == 'sgdet'
+    orc.detector.thresh = thresh
+    ref_keys = [str(k) for k in g[tag + "_keys"]]
+    assert set(orc.state_dict().keys()) == set(ref_keys), (set(orc.state_dict()) ^ set(ref_keys))
+    orc.eval()
+    nb = make_inputs(seed=17, boxes=13, rels=5)
+    t = torch.from_numpy
+    with torch.no_grad():
+        if mode == "sgdet":
+            out = orc(t(nb["imgs"]), nb["im_sizes"], 0)
+        else:
+            out = orc(t(nb["imgs"]), nb["im_sizes"], 0, t(nb["gt_boxes"]), t(nb["gt_classes"]), t(nb["gt_rels"]))
+    boxes, objs, obj_scores, rels, pred_scores = out
+    assert np.array_equal(np.asarray(objs), g[tag + "_objs"])
+    assert np.allclose(np.asarray(obj_scores), g[tag + "_obj_scores"], rtol=1e-3, atol=1e-6)
+    want_rels, want_scores = g[tag + "_rels"], g[tag + "_pred_scores"]
+    key = lambda r: r[:, 0] * 1000 + r[:, 1]
+    a, b = np.argsort(key(np.asarray(rels))), np.argsort(key(want_rels))
+    assert np.array_equal(np.asarray(rels)[a], want_rels[b])
+    assert np.abs(np.asarray(pred_scores)[a] - want_scores[b]).max() < 1e-3
