@@ -315,3 +315,24 @@ def test_oracle_baseline_configuration_matches_reference(tag, mode, thresh):
     a, b = np.argsort(key(np.asarray(rels))), np.argsort(key(want_rels))
     assert np.array_equal(np.asarray(rels)[a], want_rels[b])
     assert np.abs(np.asarray(pred_scores)[a] - want_scores[b]).max() < 1e-3
+
+
+@pytest.mark.parametrize("tag,mode,kw", [
+    ("base_sgcls", "sgcls", dict(hidden_dim=512, pooling_dim=4096, nl_obj=0, nl_edge=0, order='leftright', use_bias=True,
+                                 use_tanh=False, limit_vision=False, pass_in_obj_feats_to_decoder=False,
+                                 pass_in_obj_feats_to_edge=False)),
+    ("var_default", "predcls", {}),
+])
+def test_product_state_dict_keys_equal_the_reference_models(tag, mode, kw):
+    """The PRODUCT's RelModel (constructed on the CPU; no kernel runs) exposes exactly the state-dict keys of the
+    reference's RelModel for the scripts' baseline and the reference's default arguments (the MotifNet script
+    configuration is covered by every GPU model test, which loads one state dict into oracle and product) — checkpoints (`vgrel-*.tar`, train_rels.py:75-95) interchange."""
+    from lib.rel_model import RelModel
+    from golden.synthetic_state import CLASSES, RELS
+    g = np.load(os.path.join(ROOT, "tests", "golden", "reference_model_eval.npz"))
+    prod = RelModel(CLASSES, RELS, mode=mode, **kw)
+    ref_keys = [str(k) for k in g[tag + "_keys"]]
+    assert set(prod.state_dict().keys()) == set(ref_keys), (set(prod.state_dict()) ^ set(ref_keys))
+    if tag + "_shapes" in g:
+        shapes = {k: tuple(int(v) for v in s.split(";") if v) for k, s in zip(ref_keys, g[tag + "_shapes"])}
+        assert all(tuple(v.shape) == shapes[k] for k, v in prod.state_dict().items())
