@@ -402,7 +402,8 @@ class ObjectDetector(nn.Module):
         x = f.maxpool(f.relu(f.bn1(f.conv1(x))))
         return f.layer3(f.layer2(f.layer1(x)))
 
-    def forward(self, x, im_sizes, image_offset, gt_boxes=None, gt_classes=None, gt_rels=None, train_anchor_inds=None):
+    def forward(self, x, im_sizes, image_offset, gt_boxes=None, gt_classes=None, gt_rels=None, train_anchor_inds=None,
+                proposals=None):
         with torch.no_grad():
             fmap = self.feature_map(x)
             rel_labels = obj_labels = None
@@ -430,6 +431,15 @@ class ObjectDetector(nn.Module):
                               od_obj_labels=torch.from_numpy(l), od_box_targets=torch.from_numpy(tg),
                               od_box_priors=rois[:, 1:], rpn_scores=rpn_scores, rpn_box_deltas=rpn_box_deltas,
                               rois=rois, fmap=fmap)
+            elif self.mode == 'proposals':
+                # pre-computed proposals [n, 6] = (image, score, x1, y1, x2, y2), 2000 per image (object_detector.py:216-258,
+                # filter_roi_proposals :600-612)
+                assert proposals is not None and not self.training
+                B = len(im_sizes)
+                inds, im_per = ops.apply_nms(t2n(proposals[:, 1]), t2n(proposals[:, 2:]), 6000, 1000,
+                                             boxes_per_im=[2000] * B, nms_thresh=0.7)
+                img = np.concatenate([np.full(n, v, np.float32) for v, n in enumerate(im_per)])
+                rois = torch.from_numpy(np.concatenate((img[:, None], t2n(proposals[:, 2:])[inds]), 1).astype(np.float32))
             else:
                 rois = self.rpn_head.roi_proposals(self.rpn_head(fmap), im_sizes)
             pool = roi_align(self.compress(fmap) if self.use_resnet else fmap, rois)        # :136-137
@@ -519,12 +529,13 @@ class RelModel(nn.Module):
     def __init__(self, classes, rel_classes, mode='sgcls', embed_dim=200, hidden_dim=512, pooling_dim=4096,
                  nl_obj=2, nl_edge=4, order='leftright', thresh=0.01, use_bias=True, use_tanh=False,
                  limit_vision=False, require_overlap_det=True, pass_in_obj_feats_to_decoder=False,
-                 pass_in_obj_feats_to_edge=False):
+                 pass_in_obj_feats_to_edge=False, use_proposals=False):
         super().__init__()
         self.classes, self.rel_classes, self.mode = classes, rel_classes, mode
         self.pooling_dim, self.use_bias, self.use_tanh, self.limit_vision = pooling_dim, use_bias, use_tanh, limit_vision
         self.require_overlap = require_overlap_det and mode == 'sgdet'
-        self.detector = ObjectDetector(classes, mode='refinerels' if mode == 'sgdet' else 'gtbox', thresh=thresh)
+        self.detector = ObjectDetector(classes, mode=('proposals' if use_proposals else 'refinerels') if mode == 'sgdet'
+                                       else 'gtbox', thresh=thresh)                  # rel_model.py:340-346
         self.context = LinearizedContext(classes, rel_classes, mode, embed_dim, hidden_dim, 4096, nl_obj, nl_edge, order,
                                          pass_in_obj_feats_to_decoder, pass_in_obj_feats_to_edge)
         self.union_boxes = UnionBoxesAndFeats(7, 16, 512)
@@ -541,8 +552,8 @@ class RelModel(nn.Module):
             self.freq_bias = FrequencyBias(len(classes), len(rel_classes))
         self.masks = None
 
-    def forward(self, x, im_sizes, image_offset, gt_boxes=None, gt_classes=None, gt_rels=None):
-        result = self.detector(x, im_sizes, image_offset, gt_boxes, gt_classes, gt_rels)
+    def forward(self, x, im_sizes, image_offset, gt_boxes=None, gt_classes=None, gt_rels=None, proposals=None):
+        result = self.detector(x, im_sizes, image_offset, gt_boxes, gt_classes, gt_rels, proposals=proposals)
         im_inds = result.im_inds - image_offset
         boxes = result.rm_box_priors
         if self.training and result.rel_labels is None:

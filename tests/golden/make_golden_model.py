@@ -262,6 +262,31 @@ def main():
             out["%s_%s" % (tag, k)] = np.asarray(v)
         print(tag, "ok", np.asarray(res[3]).shape)
 
+    # ---- SGDet eval from PRE-COMPUTED proposals (use_proposals=True -> detector mode 'proposals', object_detector.py:216-258):
+    # 2000 scored boxes per image instead of the RPN
+    torch.manual_seed(0)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        m = RelModel(CLASSES, RELS, mode="sgdet", num_gpus=1, require_overlap_det=True, use_resnet=False,
+                     use_proposals=True, pass_in_obj_feats_to_decoder=False, pass_in_obj_feats_to_edge=False,
+                     rec_dropout=0.1, thresh=0.0, **KW)
+    sd = m.state_dict()
+    m.load_state_dict(synthetic_state([(k, tuple(v.shape), v.dtype) for k, v in sd.items()], seed=3))
+    m.eval()
+    nb = make_inputs(seed=19)
+    rngp = np.random.RandomState(3)
+    pb = np.concatenate([np.clip(nb["gt_boxes"] + rngp.uniform(-s_, s_, nb["gt_boxes"].shape), 0, 591) for s_ in (3, 8, 20, 40)]
+                        + [MG.rand_boxes(rngp, 2000 - 4 * nb["gt_boxes"].shape[0], lo=20.0)], 0).astype(np.float32)
+    props = np.column_stack((np.zeros(2000, np.float32), rngp.uniform(0.01, 1.0, 2000).astype(np.float32), pb)).astype(np.float32)
+    t = torch.from_numpy
+    with torch.no_grad(), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        res = m(t(nb["imgs"]), nb["im_sizes"], 0, None, None, None, t(props))
+    out["prop_proposals"] = props
+    for k, v in zip("boxes objs obj_scores rels pred_scores".split(), res):
+        out["prop_" + k] = np.asarray(v)
+    print("proposals-mode sgdet ok", np.asarray(res[3]).shape)
+
     # ---- SGDet eval: RPN head -> proposals -> NMS -> detector -> per-class NMS -> overlapping pairs -> context with the
     # decoder's overlap-aware commitments -> relation tail (detector threshold 0 so that random weights yield detections)
     torch.manual_seed(0)

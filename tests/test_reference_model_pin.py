@@ -336,3 +336,24 @@ def test_product_state_dict_keys_equal_the_reference_models(tag, mode, kw):
     if tag + "_shapes" in g:
         shapes = {k: tuple(int(v) for v in s.split(";") if v) for k, s in zip(ref_keys, g[tag + "_shapes"])}
         assert all(tuple(v.shape) == shapes[k] for k, v in prod.state_dict().items())
+
+
+def test_oracle_sgdet_eval_from_precomputed_proposals_matches_reference():
+    """`use_proposals=True`: the detector takes 2000 scored boxes per image instead of running the RPN
+    (object_detector.py:216-258, filter_roi_proposals :600-612); everything downstream as in SGDet eval."""
+    from golden.synthetic_state import make_inputs
+    g = np.load(os.path.join(ROOT, "tests", "golden", "reference_model_eval.npz"))
+    orc = script_config_oracle("sgdet", thresh=0.0)
+    orc.detector.mode = 'proposals'
+    orc.eval()
+    nb = make_inputs(seed=19)
+    with torch.no_grad():
+        boxes, objs, obj_scores, rels, pred_scores = orc(torch.from_numpy(nb["imgs"]), nb["im_sizes"], 0,
+                                                         proposals=torch.from_numpy(g["prop_proposals"]))
+    assert np.array_equal(np.asarray(objs), g["prop_objs"])
+    assert np.abs(np.asarray(boxes) - g["prop_boxes"]).max() < 1e-2
+    want_rels, want_scores = g["prop_rels"], g["prop_pred_scores"]
+    key = lambda r: r[:, 0] * 1000 + r[:, 1]
+    a, b = np.argsort(key(np.asarray(rels))), np.argsort(key(want_rels))
+    assert np.array_equal(np.asarray(rels)[a], want_rels[b])
+    assert np.abs(np.asarray(pred_scores)[a] - want_scores[b]).max() < 1e-3
