@@ -59,3 +59,26 @@ def test_variant_eval_parity(cuda, name):
     assert np.array_equal(pr[ip], or_[io])
     assert relerr(prod.last_result.rel_dists.cpu(), orc.last_result.rel_dists) < 1e-3
     assert relerr(prod.last_result.rm_obj_dists.cpu(), orc.last_result.rm_obj_dists) < 1e-3
+
+
+def test_sgdet_eval_from_precomputed_proposals_parity(cuda):
+    """use_proposals=True (detector mode 'proposals'): product vs oracle on the fixture's 2000 scored boxes."""
+    from lib.rel_model import RelModel
+    from oracle import model as OM
+    from golden.synthetic_state import synthetic_state, CLASSES, RELS, make_inputs
+    g = np.load(os.path.join(ROOT, "tests", "golden", "reference_model_eval.npz"))
+    prod = RelModel(CLASSES, RELS, mode="sgdet", num_gpus=1, require_overlap_det=True, use_resnet=False, use_proposals=True,
+                    pass_in_obj_feats_to_decoder=False, pass_in_obj_feats_to_edge=False, rec_dropout=0.1, thresh=0.0, **SCRIPT)
+    orc = OM.RelModel(CLASSES, RELS, mode="sgdet", thresh=0.0, use_proposals=True, **SCRIPT)
+    sd = orc.state_dict()
+    state = synthetic_state([(k, tuple(v.shape), v.dtype) for k, v in sd.items()], seed=3)
+    prod.load_state_dict(state); orc.load_state_dict(state)
+    prod = prod.to(cuda).eval(); orc.eval()
+    nb = make_inputs(seed=19)
+    props = torch.from_numpy(g["prop_proposals"])
+    with torch.no_grad():
+        pb, po, ps, pr, pp = prod(torch.from_numpy(nb["imgs"]).to(cuda), nb["im_sizes"], 0, None, None, None, props.to(cuda))
+        ob, oo, os_, or_, op = orc(torch.from_numpy(nb["imgs"]), nb["im_sizes"], 0, proposals=props)
+    # detections: same count, labels mostly identical (an NMS decision may flip on a near-tie of two scores)
+    assert pb.shape == ob.shape and (po == oo).mean() > 0.9
+    assert np.abs(ps - os_).max() < 5e-3
