@@ -116,6 +116,22 @@ def main():
         g["sort_%s_im" % tag], g["sort_%s_scores" % tag] = im.numpy(), scores.numpy()
         g["sort_%s_perm" % tag], g["sort_%s_inv" % tag] = perm.numpy(), inv.numpy()
         g["sort_%s_ls" % tag] = np.asarray(ls)
+    # ---- clip_grad_norm (lib/pytorch_misc.py:416-459), clipping active (max_norm 5) and inactive (1e6)
+    from lib.pytorch_misc import clip_grad_norm
+    rng = np.random.RandomState(13)
+    shapes = [(33, 7), (5,), (100, 29), (3, 3, 3)]
+    grads = [rng.randn(*sh).astype(np.float32) * 2.0 for sh in shapes]
+    for tag, mx in (("clip", 5.0), ("noclip", 1e6)):
+        ps = []
+        for i, gr in enumerate(grads):
+            p_ = torch.nn.Parameter(torch.zeros(gr.shape)); p_.grad = torch.from_numpy(gr.copy()); ps.append(("p%d" % i, p_))
+        ps.append(("nograd", torch.nn.Parameter(torch.zeros(4))))
+        total = clip_grad_norm(ps, max_norm=mx, clip=True, verbose=False)
+        g["cgn_%s_total" % tag] = np.array(float(total))
+        for i in range(len(grads)):
+            g["cgn_%s_after%d" % (tag, i)] = ps[i][1].grad.numpy().copy()
+    for i, gr in enumerate(grads):
+        g["cgn_grad%d" % i] = gr
     np.savez_compressed(os.path.join(HERE, "reference_host_ops2.npz"), **g)
     print("wrote reference_host_ops2.npz with", len(g), "arrays;",
           {k: g[k].shape for k in ("gtbox_a_rel_labels", "gtbox_b_rel_labels", "gtbox_c_rel_labels", "det_out_rois", "fd_out_rels")})

@@ -151,3 +151,18 @@ def test_forward_tuple_layout_matches_reference_blob():
         _, inds, _, _ = anchor_target_layer(gb, (h, w), rng=np.random)
         rows.append(np.column_stack((np.full(inds.shape[0], i, dtype=np.int64), inds)))
     assert np.array_equal(np.concatenate(rows, 0), g["train_anchor_inds"])
+
+
+@pytest.mark.parametrize("tag,max_norm", [("clip", 5.0), ("noclip", 1e6)])
+def test_clip_grad_norm_matches_reference(g2, tag, max_norm):
+    """lib/pytorch_misc.clip_grad_norm (one device reduction) against the reference's per-parameter loop (:416-459)."""
+    from lib.pytorch_misc import clip_grad_norm
+    ps = []
+    for i in range(4):
+        gr = g2["cgn_grad%d" % i]
+        p = torch.nn.Parameter(torch.zeros(gr.shape)); p.grad = torch.from_numpy(gr.copy()); ps.append(("p%d" % i, p))
+    ps.append(("nograd", torch.nn.Parameter(torch.zeros(4))))
+    total = clip_grad_norm(ps, max_norm=max_norm, clip=True)
+    assert abs(float(total) - float(g2["cgn_%s_total" % tag])) < 1e-5 * float(g2["cgn_%s_total" % tag])
+    for i in range(4):
+        assert np.allclose(ps[i][1].grad.numpy(), g2["cgn_%s_after%d" % (tag, i)], rtol=1e-6, atol=1e-7)
