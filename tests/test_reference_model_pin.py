@@ -359,3 +359,37 @@ def test_oracle_sgdet_eval_from_precomputed_proposals_matches_reference():
     a, b = np.argsort(key(np.asarray(rels))), np.argsort(key(want_rels))
     assert np.array_equal(np.asarray(rels)[a], want_rels[b])
     assert np.abs(np.asarray(pred_scores)[a] - want_scores[b]).max() < 1e-3
+
+
+def test_train_rels_checkpoint_loading_lines_run_against_the_product(monkeypatch):
+    """models/train_rels.py:84-95 executed against the PRODUCT on the CPU (no kernel runs): a detector checkpoint
+    (state dict of an ObjectDetector, as `vg-24.tar`) is restored into `detector.detector` with optimistic_restore and
+    its fc6 / fc7 copied into `roi_fmap[1][0|3]` and `roi_fmap_obj[0|3]` — SURVEY.md section 8b/f4."""
+    from lib.rel_model import RelModel
+    from lib.object_detector import ObjectDetector
+    from lib.pytorch_misc import optimistic_restore
+    from golden.synthetic_state import CLASSES, RELS, KW
+    monkeypatch.setattr(torch.nn.init, "orthogonal_", lambda tensor, gain=1: tensor)
+    src = ObjectDetector(CLASSES, mode='gtbox')                   # what train_detector.py saves
+    ckpt = {'state_dict': {k: v.clone() for k, v in src.state_dict().items()}, 'epoch': 24}
+    for v in ckpt['state_dict'].values():
+        if v.dtype.is_floating_point:
+            v.normal_()
+    detector = RelModel(CLASSES, RELS, mode='sgcls', num_gpus=1, pass_in_obj_feats_to_decoder=False,
+                        pass_in_obj_feats_to_edge=False, **KW)
+    assert optimistic_restore(detector.detector, ckpt['state_dict'])            # every key matched, train_rels.py:85
+    detector.roi_fmap[1][0].weight.data.copy_(ckpt['state_dict']['roi_fmap.0.weight'])
+    detector.roi_fmap[1][3].weight.data.copy_(ckpt['state_dict']['roi_fmap.3.weight'])
+    detector.roi_fmap[1][0].bias.data.copy_(ckpt['state_dict']['roi_fmap.0.bias'])
+    detector.roi_fmap[1][3].bias.data.copy_(ckpt['state_dict']['roi_fmap.3.bias'])
+    detector.roi_fmap_obj[0].weight.data.copy_(ckpt['state_dict']['roi_fmap.0.weight'])
+    detector.roi_fmap_obj[3].weight.data.copy_(ckpt['state_dict']['roi_fmap.3.weight'])
+    detector.roi_fmap_obj[0].bias.data.copy_(ckpt['state_dict']['roi_fmap.0.bias'])
+    detector.roi_fmap_obj[3].bias.data.copy_(ckpt['state_dict']['roi_fmap.3.bias'])
+    assert torch.equal(detector.detector.roi_fmap[0].weight, ckpt['state_dict']['roi_fmap.0.weight'])
+    assert torch.equal(detector.roi_fmap_obj[3].bias, ckpt['state_dict']['roi_fmap.3.bias'])
+    # the lr/10 parameter group of train_rels.py:57-61 is selected by name prefix
+    fc = [n for n, p in detector.named_parameters() if n.startswith('roi_fmap') and p.requires_grad]
+    assert len(fc) == 8 and all(n.startswith(('roi_fmap.1.', 'roi_fmap_obj.')) for n in fc)
+    # and a "vgrel" checkpoint (the whole RelModel) round-trips
+    assert optimistic_restore(detector, {k: v.clone() for k, v in detector.state_dict().items()})
