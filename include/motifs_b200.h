@@ -95,6 +95,12 @@ int mb200_bbox_overlaps_f32(const float* boxes_a, int A, const float* boxes_b, i
 /* replaces lib/fpn/box_intersections_cpu/bbox.pyx:15-62 (mode 0) and :64-107 (mode 1), float64. */
 int mb200_bbox_overlaps_f64(const double* boxes, int N, const double* query, int K, int mode, double* out,
                             cudaStream_t stream);
+/* replaces lib/fpn/anchor_targets.py:50-67: float64 IoU of N anchors x G GT boxes, per-anchor max / first arg-max,
+ * labels {-1, 0, 1} before subsampling. One warp per anchor, the IoU matrix is never materialised. All pointers DEV;
+ * gt_max_ws: G x 8 bytes of scratch (zeroed inside). */
+int mb200_anchor_targets(const double* anchors, int N, const double* gt_boxes, int G, double neg_thr, double pos_thr,
+                         unsigned long long* gt_max_ws, double* max_overlaps, int* argmax, long long* labels,
+                         cudaStream_t stream);
 /* replaces lib/get_union_boxes.py:82-87 (union roi) and the pair gather of :47. */
 int mb200_union_rois(const float* rois, const long long* pairs, int num_pairs, float* union_rois,
                      float* pair_boxes, cudaStream_t stream);
@@ -216,6 +222,10 @@ long long mb200_gemm_mn_workspace_floats(int M, int N, int K);
 int mb200_gemm_bf16x3_mn(const void* Ahi, const void* Alo, long long lda, const void* Bhi, const void* Blo, long long ldb,
                          int M, int N, int K, float* C, long long ldc, float* workspace, cudaStream_t stream);
 
+/* tcgen05 GEMM / conv kernel selection: 0 = 1-CTA kernels only, 1 = per-shape choice (default), 2 = the CTA-pair
+ * (cta_group::2, 256-row tiles) kernel whenever the shape allows. Returns the previous mode. Tests and A/B runs. */
+int mb200_gemm_set_pair_mode(int mode);
+
 /* *acc += sum_i x[i]^2 (double accumulator on the device, caller zeroes it): the global gradient norm of
  * clip_grad_norm (lib/pytorch_misc.py:416-459) as one pass per flat buffer. x 16-byte aligned. */
 int mb200_sumsq_accum(const float* x, long long n, double* acc, cudaStream_t stream);
@@ -226,6 +236,12 @@ int mb200_sumsq_accum(const float* x, long long n, double* acc, cudaStream_t str
 int mb200_sgd_momentum_clip(float* params, float* grads, float* momentum_buf, long long n, float lr, float momentum,
                             float weight_decay, const float* total_norm_dev, float max_norm, int first_step,
                             int zero_grad, cudaStream_t stream);
+/* Same, with `grads` holding grad_scale^-1 times the gradient (data parallel: the all-reduced SUM and
+ * grad_scale = 1/world, which saves the separate averaging pass over the 1.1 GB buffer); *total_norm_dev is the
+ * norm of the SCALED gradient. */
+int mb200_sgd_momentum_clip_scaled(float* params, float* grads, float* momentum_buf, long long n, float lr, float momentum,
+                                   float weight_decay, const float* total_norm_dev, float max_norm, float grad_scale,
+                                   int first_step, int zero_grad, cudaStream_t stream);
 
 #ifdef __cplusplus
 }

@@ -147,6 +147,72 @@ inline int grid_for(long long total, int threads) {
   return (int)(b < 1 ? 1 : (b > cap ? cap : b));
 }
 
+
+// ------------------------------------------------------------------ RPN anchor-target assignment
+// lib/fpn/anchor_targets.py:50-67 of the reference (numpy in the DataLoader worker): IoU of every inside-image
+// anchor with every GT box in float64 (bbox.pyx:21-62), per-anchor max / FIRST arg-max (np.argmax), per-GT-box
+// max, then labels: 0 where max < neg_thr, 1 where the anchor attains some GT box's maximum (`overlaps ==
+// gt_max_overlaps`, which also fires for a GT box that no anchor overlaps: every anchor then "attains" 0),
+// 1 where max >= pos_thr; -1 otherwise. One WARP per anchor, lanes stride over the GT boxes; the [N,G] IoU
+// matrix is never written (27 380 x G doubles in the reference). Pass 1: shuffle reduce (value, then lower
+// index) + the column maxima through 64-bit atomicMax on the bit pattern (IoU >= 0, so the unsigned order of
+// the bits is the order of the values). Pass 2 re-derives each IoU bit-identically and votes with __any_sync.
+__device__ __forceinline__ double iou_f64(const double* __restrict__ bb, const double* __restrict__ qq) {
+  const double iw = fmin(bb[2], qq[2]) - fmax(bb[0], qq[0]) + 1;
+  if (!(iw > 0)) return 0.0;
+  const double ih = fmin(bb[3], qq[3]) - fmax(bb[1], qq[1]) + 1;
+  if (!(ih > 0)) return 0.0;
+  const double box_area = __dmul_rn(qq[2] - qq[0] + 1, qq[3] - qq[1] + 1);
+  const double inter = __dmul_rn(iw, ih);
+  const double ua = __dadd_rn(__dadd_rn(__dmul_rn(bb[2] - bb[0] + 1, bb[3] - bb[1] + 1), box_area), -inter);
+  return __ddiv_rn(inter, ua);
+}
+
+__global__ void anchor_rowmax_kernel(const double* __restrict__ anchors, int N, const double* __restrict__ gt, int G,
+                                     double* __restrict__ max_ov, int* __restrict__ argmax,
+                                     unsigned long long* __restrict__ gt_max_bits) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (blockDim.x >> 5) * gridDim.x;
+  for (int a = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); a < N; a += warps) {
+    const double* bb = anchors + (size_t)a * 4;
+    double best = -1.0; int arg = 0x7fffffff;
+    for (int g = lane; g < G; g += 32) {
+      const double v = iou_f64(bb, gt + (size_t)g * 4);
+      if (v > best) { best = v; arg = g; }                      // strict: the first maximum of this lane's stride
+      if (v > 0.0) atomicMax(gt_max_bits + g, (unsigned long long)__double_as_longlong(v));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+      if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+    }
+    if (lane == 0) { max_ov[a] = best; argmax[a] = arg; }
+  }
+}
+
+__global__ void anchor_label_kernel(const double* __restrict__ anchors, int N, const double* __restrict__ gt, int G,
+                                    const double* __restrict__ max_ov, const unsigned long long* __restrict__ gt_max_bits,
+                                    double neg_thr, double pos_thr, long long* __restrict__ labels) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (blockDim.x >> 5) * gridDim.x;
+  for (int a = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); a < N; a += warps) {
+    const double* bb = anchors + (size_t)a * 4;
+    bool hit = false;
+    for (int g = lane; g < G; g += 32)
+      hit |= (iou_f64(bb, gt + (size_t)g * 4) == __longlong_as_double((long long)gt_max_bits[g]));
+    hit = __any_sync(0xffffffffu, hit);
+    if (lane == 0) {
+      const double m = max_ov[a];
+      long long l = -1;
+      if (m < neg_thr) l = 0;
+      if (hit) l = 1;
+      if (m >= pos_thr) l = 1;
+      labels[a] = l;
+    }
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -166,6 +232,20 @@ int mb200_bbox_overlaps_f64(const double* boxes, int N, const double* query, int
   if (mode != 0 && mode != 1) return MB200_ERR_ARG;
   bbox_overlaps_f64_kernel<<<grid_for((long long)N * K, 256), 256, 0, stream>>>(boxes, N, query, K, mode, out);
   MB200_CHECK_LAUNCH("mb200_bbox_overlaps_f64");
+  return MB200_OK;
+}
+
+int mb200_anchor_targets(const double* anchors, int N, const double* gt_boxes, int G, double neg_thr, double pos_thr,
+                         unsigned long long* gt_max_ws, double* max_overlaps, int* argmax, long long* labels,
+                         cudaStream_t stream) {
+  if (N <= 0) return MB200_OK;
+  if (G <= 0) return MB200_ERR_ARG;
+  MB200_CHECK(cudaMemsetAsync(gt_max_ws, 0, sizeof(unsigned long long) * (size_t)G, stream));
+  const int blocks = min(mb200_div_up(N, 8), kNumSMs * 8);
+  anchor_rowmax_kernel<<<blocks, 256, 0, stream>>>(anchors, N, gt_boxes, G, max_overlaps, argmax, gt_max_ws);
+  MB200_CHECK_LAUNCH("anchor_rowmax_kernel");
+  anchor_label_kernel<<<blocks, 256, 0, stream>>>(anchors, N, gt_boxes, G, max_overlaps, gt_max_ws, neg_thr, pos_thr, labels);
+  MB200_CHECK_LAUNCH("anchor_label_kernel");
   return MB200_OK;
 }
 

@@ -272,6 +272,241 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_const
   if (warp == 1) { tc::tc_fence_after(); tc::tmem_dealloc(tmem_base, TMEM_COLS); }
 }
 
+
+// ====================================================================================== CTA-pair variant
+// Same pipeline with cta_group::2 (tc_common.cuh "CTA pair"): a cluster of two CTAs computes a 256 x BN tile with ONE
+// tcgen05.mma (M = 256) per k step and operand pair. CTA r of the pair owns rows [128 r, 128 r + 128) of the tile
+// (conv: spatial tile 2*pm + r), loads its own A tiles and HALF of the B tile (rows [r*BN/2, (r+1)*BN/2) of the
+// weights), and drains its own half of the accumulator. Per SM and k-block: 32 KB of A + 2 * BN/2 * 128 B of B land in
+// shared memory instead of 32 KB + 2 * BN * 128 B, and each MMA reads BN/2 instead of BN rows of B per SM — the
+// 1-CTA kernel sits at 54-73 % tensor pipe with its shared-memory pipe saturated (profiles/r01_SUMMARY.md).
+// Barriers: full[s] of the LEADER counts one arrive.expect_tx (2 * stage bytes) and receives the TMA bytes of both
+// CTAs; empty[s] / tfull[a] exist in both CTAs and are signalled by multicast commits; tempty[a] of the leader
+// collects the 8 epilogue warps of the pair.
+template <int BN_> struct Cfg2 {
+  static constexpr int BN = BN_;
+  static constexpr int HALF_B = (BN_ / 2) * BK * 2;              // bytes of one B operand half-tile
+  static constexpr int STAGE_BYTES = 2 * TILE_A + 2 * HALF_B;    // per CTA
+  static constexpr int STAGES = (BN_ == 256) ? 3 : 4;
+  static constexpr int TMEM_COLS = ACC_STAGES * BN_;
+  static constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+// pair-tile t -> coordinates of THIS CTA's half (rank r): p.m_tiles counts 128-row tiles, pairs walk ceil(m_tiles / 2)
+template <int BN>
+__device__ __forceinline__ TileCoord decode_tile2(const Params& p, int t, int rank, int pm_tiles) {
+  TileCoord tc_;
+  const int per_split = pm_tiles * p.n_tiles;
+  tc_.split = t / per_split;
+  const int r = t - tc_.split * per_split;
+  int pmi, ni;
+  if (p.m_fastest) { ni = r / pm_tiles; pmi = r - ni * pm_tiles; }
+  else { pmi = r / p.n_tiles; ni = r - pmi * p.n_tiles; }
+  const int mi = 2 * pmi + rank;                 // may equal p.m_tiles for the last pair: all rows masked, TMA zero fill
+  tc_.n0 = ni * BN;
+  tc_.m0 = mi * BM; tc_.img = 0; tc_.h0 = 0; tc_.w0 = 0;
+  if (p.conv) {
+    const int per_img = p.tiles_w * p.tiles_h;
+    tc_.img = mi / per_img;                      // == B for the dummy half: out of bounds in the image dimension
+    const int q = mi - tc_.img * per_img;
+    const int th = q / p.tiles_w;
+    tc_.h0 = th * TH;
+    tc_.w0 = (q - th * p.tiles_w) * TW;
+  }
+  return tc_;
+}
+
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+gemm_bf16x3_2cta_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant__ CUtensorMap tmAlo,
+                        const __grid_constant__ CUtensorMap tmBhi, const __grid_constant__ CUtensorMap tmBlo,
+                        const Params p, const int num_images) {
+  constexpr int STAGES = Cfg2<BN>::STAGES, HALF_B = Cfg2<BN>::HALF_B, STAGE_BYTES = Cfg2<BN>::STAGE_BYTES;
+  constexpr int TMEM_COLS = Cfg2<BN>::TMEM_COLS;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = (uint64_t*)(smem + (size_t)STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + ACC_STAGES;
+  uint32_t* tmem_slot = (uint32_t*)(tempty_bar + ACC_STAGES);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = tc::cluster_ctarank();
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int pm_tiles = (p.m_tiles + 1) >> 1;
+  const int total_tiles = p.splits * pm_tiles * p.n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    tc::prefetch_tmap(&tmAhi); tc::prefetch_tmap(&tmAlo); tc::prefetch_tmap(&tmBhi); tc::prefetch_tmap(&tmBlo);
+    for (int s = 0; s < STAGES; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < ACC_STAGES; ++s) { tc::mbar_init(&tfull_bar[s], 1); tc::mbar_init(&tempty_bar[s], 8); }
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) tc::tmem_alloc_2sm(tmem_slot, TMEM_COLS);
+  tc::tc_fence_before();
+  tc::cluster_sync_all();                       // barriers of BOTH CTAs initialised before any remote arrive / TMA
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------------------------------------------------------- TMA producer (both CTAs)
+      int stage = 0; uint32_t phase = 0;
+      const int cblocks = p.conv ? p.Cin / BK : 0;
+      for (int t = pair; t < total_tiles; t += npairs) {
+        const TileCoord tl = decode_tile2<BN>(p, t, (int)rank, pm_tiles);
+        const int kb0 = tl.split * p.kblocks;
+        const int nrow = tl.n0 + (int)rank * (BN / 2);          // this CTA's half of the B tile
+        for (int kb = 0; kb < p.kblocks; ++kb) {
+          tc::mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* st = smem + (size_t)stage * STAGE_BYTES;
+          if (rank == 0) tc::mbar_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
+          const uint32_t fb = tc::mapa_shared(tc::smem_u32(&full_bar[stage]), 0);
+          const int kg = kb0 + kb;
+          if (!p.conv) {
+            tc::tma_load_2d_2sm(st, &tmAhi, fb, kg * BK, tl.m0);
+            tc::tma_load_2d_2sm(st + TILE_A, &tmAlo, fb, kg * BK, tl.m0);
+          } else {
+            const int tap = kg / cblocks, cb = kg - tap * cblocks;
+            const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
+            tc::tma_load_4d_2sm(st, &tmAhi, fb, cb * BK, tl.w0 + dx, tl.h0 + dy, tl.img);
+            tc::tma_load_4d_2sm(st + TILE_A, &tmAlo, fb, cb * BK, tl.w0 + dx, tl.h0 + dy, tl.img);
+          }
+          tc::tma_load_2d_2sm(st + 2 * TILE_A, &tmBhi, fb, kg * BK, nrow);
+          tc::tma_load_2d_2sm(st + 2 * TILE_A + HALF_B, &tmBlo, fb, kg * BK, nrow);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      // ---------------------------------------------------------------- MMA issuer (leader CTA only)
+      constexpr uint32_t idesc = tc::umma_idesc_bf16_f32(2 * BM, BN);
+      int stage = 0; uint32_t phase = 0;
+      int it = 0;
+      for (int t = pair; t < total_tiles; t += npairs, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        tc::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);      // both CTAs' epilogues have drained this accumulator
+        tc::tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < p.kblocks; ++kb) {
+          tc::mbar_wait(&full_bar[stage], phase);            // bytes of BOTH CTAs have landed
+          tc::tc_fence_after();
+          const uint32_t sa = tc::smem_u32(smem + (size_t)stage * STAGE_BYTES);
+          const uint64_t a_hi = tc::umma_desc_k_sw128(sa), a_lo = tc::umma_desc_k_sw128(sa + TILE_A);
+          const uint64_t b_hi = tc::umma_desc_k_sw128(sa + 2 * TILE_A), b_lo = tc::umma_desc_k_sw128(sa + 2 * TILE_A + HALF_B);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t adv = (uint64_t)((k * 16 * 2) >> 4);
+            tc::umma_bf16_2sm(tmem_d, a_hi + adv, b_hi + adv, idesc, (kb | k) != 0);
+            tc::umma_bf16_2sm(tmem_d, a_hi + adv, b_lo + adv, idesc, 1);
+            tc::umma_bf16_2sm(tmem_d, a_lo + adv, b_hi + adv, idesc, 1);
+          }
+          tc::umma_commit_2sm(&empty_bar[stage], 3);          // frees the slot in both CTAs
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc::umma_commit_2sm(&tfull_bar[acc], 3);              // accumulator complete -> both epilogues
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 2..5 of both CTAs)
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const uint32_t tempty_leader0 = tc::mapa_shared(tc::smem_u32(&tempty_bar[0]), 0);
+    int it = 0;
+    for (int t = pair; t < total_tiles; t += npairs, ++it) {
+      const TileCoord tl = decode_tile2<BN>(p, t, (int)rank, pm_tiles);
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      tc::mbar_wait(&tfull_bar[acc], acc_phase);
+      tc::tc_fence_after();
+      long long row;
+      if (!p.conv) {
+        row = (tl.m0 + r < p.M) ? (long long)(tl.m0 + r) : -1;
+      } else {
+        const int h = tl.h0 + r / TW, w = tl.w0 + (r % TW);
+        row = (tl.img < num_images && h < p.H && w < p.W) ? ((long long)tl.img * p.H + h) * p.W + w : -1;
+      }
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        __syncwarp();
+        uint32_t v[32];
+        tc::tmem_ld_32x32(taddr + (uint32_t)(c * 32), v);
+        tc::tmem_ld_wait();
+        const int nb = tl.n0 + c * 32;
+        if (row < 0 || nb >= p.N) continue;
+        const int ncols = min(32, p.N - nb);
+        if (p.splits > 1) {
+          float* dst = p.partial + ((size_t)tl.split * p.M + row) * p.N + nb;
+          if (ncols == 32 && ((((uintptr_t)dst) & 15) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) ((uint4*)dst)[j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (j < ncols) dst[j] = __uint_as_float(v[j]);
+          }
+          continue;
+        }
+        float x[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float tt = __uint_as_float(v[j]);
+          if (p.bias && j < ncols) tt += __ldg(p.bias + nb + j);
+          if (p.relu) tt = fmaxf(tt, 0.f);
+          x[j] = tt;
+        }
+        if (p.C) {
+          float* dst = p.C + row * p.ldc + nb;
+          if (ncols == 32 && ((((uintptr_t)dst) & 15) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) ((float4*)dst)[j] = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (j < ncols) dst[j] = x[j];
+          }
+        }
+        if (p.Chi) {
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float a0 = x[2 * j], a1 = x[2 * j + 1];
+            const __nv_bfloat16 h0 = __float2bfloat16_rn(a0), h1 = __float2bfloat16_rn(a1);
+            hi[j] = pack_bf16x2(a0, a1);
+            lo[j] = pack_bf16x2(a0 - __bfloat162float(h0), a1 - __bfloat162float(h1));
+          }
+          __nv_bfloat16* dh = p.Chi + row * p.ldsplit + nb;
+          __nv_bfloat16* dl = p.Clo + row * p.ldsplit + nb;
+          if (ncols == 32 && ((((uintptr_t)dh) & 15) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              ((uint4*)dh)[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+              ((uint4*)dl)[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (j < ncols) {
+              __nv_bfloat16 h, l; tc::split_bf16(x[j], h, l);
+              dh[j] = h; dl[j] = l;
+            }
+          }
+        }
+      }
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive_cluster(tempty_leader0 + (uint32_t)(acc * sizeof(uint64_t)));
+    }
+  }
+  // neither CTA may leave (or free TMEM) while the other can still signal its barriers / read its shared memory
+  tc::tc_fence_before();
+  tc::cluster_sync_all();
+  if (warp == 1) { tc::tc_fence_after(); tc::tmem_dealloc_2sm(tmem_base, TMEM_COLS); }
+}
+
 // split-K second pass: out = sum_z partial[z] (+ bias) (relu) -> fp32 and/or split bf16
 __global__ void splitk_reduce_kernel(const float* __restrict__ partial, int splits, long long MN, int N,
                                      const float* __restrict__ bias, int relu, float* __restrict__ C, long long ldc,
@@ -335,32 +570,76 @@ int ensure_attr() {
   if (!done) {
     MB200_CHECK(cudaFuncSetAttribute(gemm_bf16x3_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<128>::SMEM_BYTES));
     MB200_CHECK(cudaFuncSetAttribute(gemm_bf16x3_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<256>::SMEM_BYTES));
+    MB200_CHECK(cudaFuncSetAttribute(gemm_bf16x3_2cta_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg2<128>::SMEM_BYTES));
+    MB200_CHECK(cudaFuncSetAttribute(gemm_bf16x3_2cta_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg2<256>::SMEM_BYTES));
     done = true;
   }
   return MB200_OK;
+}
+
+// 0: 1-CTA kernels only; 1: choose per shape (default); 2: CTA-pair kernel whenever the shape allows (tests, A/B runs)
+int g_pair_mode = 1;
+
+inline double wave_eff(long long tiles, int slots) {
+  return (double)tiles / (double)(((tiles + slots - 1) / slots) * slots);
 }
 
 // Tile width for an N-wide output: 128x256 tiles move 27 % fewer operand bytes per flop, but the
 // persistent grid is quantised in waves of one tile per SM — weigh both.
 inline int pick_bn(long long m_tiles, int N) {
   if (N < 256) return 128;
-  auto eff = [](long long tiles) { return (double)tiles / (double)(((tiles + kNumSMs - 1) / kNumSMs) * kNumSMs); };
   const long long t128 = m_tiles * ((N + 127) / 128), t256 = m_tiles * ((N + 255) / 256);
   const double waste256 = (double)N / (double)(((N + 255) / 256) * 256);     // column padding
   const double waste128 = (double)N / (double)(((N + 127) / 128) * 128);
-  return (eff(t256) * waste256 * 1.3 > eff(t128) * waste128) ? 256 : 128;
+  return (wave_eff(t256, kNumSMs) * waste256 * 1.3 > wave_eff(t128, kNumSMs) * waste128) ? 256 : 128;
+}
+
+// CTA-pair plan for m_tiles 128-row tiles and an N-wide output: BN (0 = use the 1-CTA kernel). The pair kernel
+// runs the tensor pipe faster per tile (operand delivery no longer binds) but needs >= 2 row tiles and
+// quantises in waves of 74 pair-tiles.
+inline int pick_pair_bn(long long m_tiles, int N, int splits, int bn1) {
+  if (g_pair_mode == 0 || m_tiles < 2 || splits > 1) return 0;
+  const long long pm = (m_tiles + 1) / 2;
+  const int pairs = kNumSMs / 2;
+  const double rows = (double)m_tiles / (double)(2 * pm);                     // the dummy half of an odd last pair
+  double best = 0.0; int best_bn = 0;
+  for (int bn = 128; bn <= 256; bn += 128) {
+    if (bn == 256 && N < 256) continue;
+    const double colw = (double)N / (double)(((N + bn - 1) / bn) * bn);
+    const double e = wave_eff(pm * ((N + bn - 1) / bn), pairs) * colw * rows * (bn == 256 ? 1.0 : 0.93);
+    if (e > best) { best = e; best_bn = bn; }
+  }
+  if (g_pair_mode == 2) return best_bn;
+  const double colw1 = (double)N / (double)(((N + bn1 - 1) / bn1) * bn1);
+  const double e1 = wave_eff(m_tiles * ((N + bn1 - 1) / bn1), kNumSMs) * colw1;
+  return (best * 1.15 > e1) ? best_bn : 0;
 }
 
 int launch(const CUtensorMap& ahi, const CUtensorMap& alo, const CUtensorMap& bhi, const CUtensorMap& blo,
-           const Params& p, int bn, cudaStream_t stream) {
+           const Params& p, int bn, int pair_bn, int num_images, cudaStream_t stream) {
   int rc = ensure_attr();
   if (rc != MB200_OK) return rc;
+  if (pair_bn) {
+    const long long tiles = (long long)p.splits * ((p.m_tiles + 1) / 2) * p.n_tiles;
+    if (tiles > 0x7fffffffLL) return MB200_ERR_UNSUPPORTED;
+    const int grid = 2 * (int)min(tiles, (long long)(kNumSMs / 2));         // persistent: one CTA pair per TPC
+    if (pair_bn == 256)
+      gemm_bf16x3_2cta_kernel<256><<<grid, kGemmThreads, Cfg2<256>::SMEM_BYTES, stream>>>(ahi, alo, bhi, blo, p, num_images);
+    else
+      gemm_bf16x3_2cta_kernel<128><<<grid, kGemmThreads, Cfg2<128>::SMEM_BYTES, stream>>>(ahi, alo, bhi, blo, p, num_images);
+    MB200_CHECK_LAUNCH("gemm_bf16x3_2cta_kernel");
+    return MB200_OK;
+  }
   const long long tiles = (long long)p.splits * p.m_tiles * p.n_tiles;
   if (tiles > 0x7fffffffLL) return MB200_ERR_UNSUPPORTED;
   const int grid = (int)min(tiles, (long long)kNumSMs);      // persistent: one CTA per SM
   if (bn == 256) gemm_bf16x3_kernel<256><<<grid, kGemmThreads, Cfg<256>::SMEM_BYTES, stream>>>(ahi, alo, bhi, blo, p);
   else gemm_bf16x3_kernel<128><<<grid, kGemmThreads, Cfg<128>::SMEM_BYTES, stream>>>(ahi, alo, bhi, blo, p);
   MB200_CHECK_LAUNCH("gemm_bf16x3_kernel");
+  return MB200_OK;
+}
+
+int finish_splitk(const Params& p, cudaStream_t stream) {
   if (p.splits > 1) {
     const long long MN = (long long)p.M * p.N;
     const int blocks = (int)min((long long)kNumSMs * 8, (MN + 255) / 256);
@@ -404,20 +683,23 @@ int mb200_gemm_bf16x3(const void* Ahi, const void* Alo, const void* Bhi, const v
     if (ws > 0) p.splits = (int)(ws / ((long long)M * N));
   }
   const int bn = p.splits > 1 ? 128 : pick_bn(mb200_div_up(M, BM), N);
+  const int pair_bn = pick_pair_bn(mb200_div_up(M, BM), N, p.splits, bn);
+  const int box_b = pair_bn ? pair_bn / 2 : bn;
   if (!make_tmap_2d(&ta, Ahi, M, Kp, BM) || !make_tmap_2d(&tal, Alo, M, Kp, BM) ||
-      !make_tmap_2d(&tb, Bhi, N, Kp, bn) || !make_tmap_2d(&tbl, Blo, N, Kp, bn)) {
+      !make_tmap_2d(&tb, Bhi, N, Kp, box_b) || !make_tmap_2d(&tbl, Blo, N, Kp, box_b)) {
     mb200_set_error("cuTensorMapEncodeTiled", cudaErrorInvalidValue);
     return MB200_ERR_CUDA;
   }
   p.kblocks = kblocks / p.splits;
   p.C = C; p.ldc = ldc; p.Chi = (__nv_bfloat16*)Chi; p.Clo = (__nv_bfloat16*)Clo; p.ldsplit = ldsplit;
   p.bias = bias; p.relu = relu; p.partial = workspace; p.conv = 0;
-  p.m_tiles = mb200_div_up(M, BM); p.n_tiles = mb200_div_up(N, bn);
+  p.m_tiles = mb200_div_up(M, BM); p.n_tiles = mb200_div_up(N, pair_bn ? pair_bn : bn);
   // ncu: fc6 dX / dW re-streamed the 150-400 MB B operand once per m-tile (2.7 / 3.3 GB of DRAM reads).
   // When A (hi+lo) fits comfortably in L2 and B is the larger operand, walk m fastest instead.
   const double a_bytes = 4.0 * M * Kp, b_bytes = 4.0 * N * Kp;
   p.m_fastest = (a_bytes <= 48e6 && b_bytes > a_bytes) ? 1 : 0;
-  return launch(ta, tal, tb, tbl, p, bn, stream);
+  int rc = launch(ta, tal, tb, tbl, p, bn, pair_bn, 0, stream);
+  return rc != MB200_OK ? rc : finish_splitk(p, stream);
 }
 
 // 3x3 / stride 1 / pad 1 convolution as implicit GEMM. x: NHWC bf16 pair [B,H,W,Cin] (Cin % 64 == 0);
@@ -429,9 +711,12 @@ int mb200_conv3x3_bf16x3(const void* xhi, const void* xlo, const void* whi, cons
   if (Cin % BK != 0) return MB200_ERR_ARG;
   CUtensorMap ta, tal, tb, tbl;
   const long long Kp = 9LL * Cin;
-  const int bn = pick_bn((long long)B * mb200_div_up(W, TW) * mb200_div_up(H, TH), Cout);
+  const long long sp_tiles = (long long)B * mb200_div_up(W, TW) * mb200_div_up(H, TH);
+  const int bn = pick_bn(sp_tiles, Cout);
+  const int pair_bn = pick_pair_bn(sp_tiles, Cout, 1, bn);
+  const int box_b = pair_bn ? pair_bn / 2 : bn;
   if (!make_tmap_nhwc(&ta, xhi, B, H, W, Cin) || !make_tmap_nhwc(&tal, xlo, B, H, W, Cin) ||
-      !make_tmap_2d(&tb, whi, Cout, Kp, bn) || !make_tmap_2d(&tbl, wlo, Cout, Kp, bn)) {
+      !make_tmap_2d(&tb, whi, Cout, Kp, box_b) || !make_tmap_2d(&tbl, wlo, Cout, Kp, box_b)) {
     mb200_set_error("cuTensorMapEncodeTiled", cudaErrorInvalidValue);
     return MB200_ERR_CUDA;
   }
@@ -440,8 +725,16 @@ int mb200_conv3x3_bf16x3(const void* xhi, const void* xlo, const void* whi, cons
   p.C = y; p.ldc = Cout; p.Chi = (__nv_bfloat16*)yhi; p.Clo = (__nv_bfloat16*)ylo; p.ldsplit = Cout;
   p.bias = bias; p.relu = relu; p.partial = nullptr;
   p.conv = 1; p.H = H; p.W = W; p.Cin = Cin; p.tiles_w = mb200_div_up(W, TW); p.tiles_h = mb200_div_up(H, TH);
-  p.m_tiles = B * p.tiles_w * p.tiles_h; p.n_tiles = mb200_div_up(Cout, bn);
-  return launch(ta, tal, tb, tbl, p, bn, stream);
+  p.m_tiles = B * p.tiles_w * p.tiles_h; p.n_tiles = mb200_div_up(Cout, pair_bn ? pair_bn : bn);
+  return launch(ta, tal, tb, tbl, p, bn, pair_bn, B, stream);
+}
+
+/* 0: 1-CTA kernels only; 1: per-shape choice (default); 2: the CTA-pair (cta_group::2) kernel whenever the shape allows.
+ * Returns the previous mode. For tests and A/B measurements. */
+int mb200_gemm_set_pair_mode(int mode) {
+  const int old = g_pair_mode;
+  if (mode >= 0 && mode <= 2) g_pair_mode = mode;
+  return old;
 }
 
 }  // extern "C"

@@ -10,13 +10,16 @@ namespace {
 
 __global__ void sgd_momentum_clip_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ buf,
                                          long long n, float lr, float momentum, float weight_decay,
-                                         const float* __restrict__ total_norm, float max_norm, int first_step,
-                                         int zero_grad) {
+                                         const float* __restrict__ total_norm, float max_norm, float grad_scale,
+                                         int first_step, int zero_grad) {
+  // g holds grad_scale^-1 times the gradient (data parallel: the all-reduced SUM, grad_scale = 1/world);
+  // *total_norm is the norm of the SCALED gradient.
   float coef = 1.f;
   if (total_norm) {                       // clip_coef = max_norm / (norm + 1e-6), applied when < 1
     const float c = max_norm / (*total_norm + 1e-6f);
     coef = c < 1.f ? c : 1.f;
   }
+  coef *= grad_scale;
   const long long n4 = n >> 2;
   const long long stride = (long long)blockDim.x * gridDim.x;
   float4* p4 = (float4*)p; float4* g4 = (float4*)g; float4* b4 = (float4*)buf;
@@ -105,14 +108,22 @@ extern "C" int mb200_sumsq_accum(const float* x, long long n, double* acc, cudaS
   return MB200_OK;
 }
 
-extern "C" int mb200_sgd_momentum_clip(float* params, float* grads, float* momentum_buf, long long n, float lr,
-                                       float momentum, float weight_decay, const float* total_norm_dev,
-                                       float max_norm, int first_step, int zero_grad, cudaStream_t stream) {
+extern "C" int mb200_sgd_momentum_clip_scaled(float* params, float* grads, float* momentum_buf, long long n, float lr,
+                                              float momentum, float weight_decay, const float* total_norm_dev,
+                                              float max_norm, float grad_scale, int first_step, int zero_grad,
+                                              cudaStream_t stream) {
   if (n <= 0) return MB200_OK;
   if ((((uintptr_t)params) | ((uintptr_t)grads) | ((uintptr_t)momentum_buf)) & 15) return MB200_ERR_ARG;
   const int blocks = (int)min((long long)kNumSMs * 8, (n / 4 + 255) / 256 + 1);
   sgd_momentum_clip_kernel<<<blocks, 256, 0, stream>>>(params, grads, momentum_buf, n, lr, momentum, weight_decay,
-                                                       total_norm_dev, max_norm, first_step, zero_grad);
+                                                       total_norm_dev, max_norm, grad_scale, first_step, zero_grad);
   MB200_CHECK_LAUNCH("mb200_sgd_momentum_clip");
   return MB200_OK;
+}
+
+extern "C" int mb200_sgd_momentum_clip(float* params, float* grads, float* momentum_buf, long long n, float lr,
+                                       float momentum, float weight_decay, const float* total_norm_dev,
+                                       float max_norm, int first_step, int zero_grad, cudaStream_t stream) {
+  return mb200_sgd_momentum_clip_scaled(params, grads, momentum_buf, n, lr, momentum, weight_decay, total_norm_dev,
+                                        max_norm, 1.f, first_step, zero_grad, stream);
 }

@@ -2,11 +2,9 @@
 path (`models/train_detector.py:78-155` trains the VGG backbone and the RPN head, so gradients
 must flow through `features` and `rpn_head.conv`, lib/object_detector.py:110-127, 521-531).
 
-STATUS: experimental. The gradient formulas below are pinned on the CPU against torch autograd through a torch
-backend with the same three primitives (tests/test_conv_tc_walk.py); the kernel backend reuses kernels that are
-parity-green on the GPU (implicit-GEMM conv, transposed im2col, bf16x3 GEMM) but this composition has not run on a
-B200 yet, so `ObjectDetector.feature_map` keeps raising for a trainable backbone unless
-MOTIFS_EXPERIMENTAL_DETECTOR_TRAIN=1.
+STATUS: the gradient formulas below are pinned on the CPU against torch autograd through a torch backend with the same
+three primitives (tests/test_conv_tc_walk.py); the kernel backend reuses kernels that are parity-green on the GPU
+(implicit-GEMM conv, transposed im2col, bf16x3 GEMM) and is held to fp64 on a B200 by tests/test_detector_train_gpu.py.
 
 Everything is NHWC fp32 at the Function boundary. Three primitives, supplied by a backend:
     conv3x3(x [B,H,W,Ci], wmat [Co, 9*Ci] (k = (kh*3+kw)*Ci + ci), bias|None, relu) -> [B,H,W,Co]

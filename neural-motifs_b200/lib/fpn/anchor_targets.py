@@ -1,14 +1,16 @@
 """RPN anchor-target assignment — lib/fpn/anchor_targets.py:16-105 of the reference (numpy in
-the DataLoader collate there). Here the 27 380 x G float64 IoU runs on the device
-(`mb200_bbox_overlaps_f64`, bit-identical to bbox.pyx) and the arg-max / labelling is done with
-torch on the device; only the fg/bg subsampling (npr.choice, injectable) stays on the host."""
+the DataLoader collate there). Here the 27 380 x G float64 IoU, the per-anchor max / first arg-max,
+the per-GT maxima and the labelling run as two warp-per-anchor kernels (`mb200_anchor_targets`,
+csrc/boxes.cu: shuffle reductions, 64-bit atomicMax for the column maxima, the IoU matrix is never
+written); results are bit-identical to bbox.pyx + numpy. Only the fg/bg subsampling (npr.choice,
+injectable, consumed in the reference's order) stays on the host."""
 import numpy as np
 import numpy.random as npr
 import torch
 
 from config import IM_SCALE, RPN_NEGATIVE_OVERLAP, RPN_POSITIVE_OVERLAP, RPN_BATCHSIZE, RPN_FG_FRACTION, \
     ANCHOR_SIZE, ANCHOR_SCALES, ANCHOR_RATIOS
-from lib.fpn.box_intersections_cpu.bbox import bbox_overlaps_cuda
+import motifs_cabi as _c
 from lib.fpn.generate_anchors import generate_anchors
 
 _ANCHORS = None
@@ -20,6 +22,24 @@ def _anchors():
         _ANCHORS = generate_anchors(base_size=ANCHOR_SIZE, feat_stride=16, anchor_scales=ANCHOR_SCALES,
                                     anchor_ratios=ANCHOR_RATIOS)
     return _ANCHORS
+
+
+def anchor_labels_device(anchors, gt_boxes, neg_thr=RPN_NEGATIVE_OVERLAP, pos_thr=RPN_POSITIVE_OVERLAP):
+    """anchors [N,4], gt_boxes [G,4] float64 CUDA -> (labels int64 [N] in {-1,0,1} before subsampling, first arg-max
+    int32 [N], max overlap float64 [N]), all on the device (anchor_targets.py:50-67)."""
+    _c.require_cuda(anchors, gt_boxes)
+    a = anchors.contiguous().double(); g = gt_boxes.contiguous().double()
+    N, G = a.size(0), g.size(0)
+    dev = a.device
+    labels = torch.empty(N, dtype=torch.long, device=dev)
+    arg = torch.empty(N, dtype=torch.int32, device=dev)
+    mx = torch.empty(N, dtype=torch.float64, device=dev)
+    ws = torch.empty(max(G, 1), dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        rc = _c.load().mb200_anchor_targets(_c.ptr(a), N, _c.ptr(g), G, float(neg_thr), float(pos_thr), _c.ptr(ws),
+                                            _c.ptr(mx), _c.ptr(arg), _c.ptr(labels), _c.cur_stream())
+    _c.check(rc, "mb200_anchor_targets")
+    return labels, arg, mx
 
 
 def anchor_target_layer(gt_boxes, im_size, allowed_border=0, rng=npr):
@@ -34,18 +54,10 @@ def anchor_target_layer(gt_boxes, im_size, allowed_border=0, rng=npr):
     if good.size == 0:
         raise ValueError("There were no good anchors for an image of size {} with boxes {}".format(im_size, gt_boxes))
     gt_boxes = np.asarray(gt_boxes)
-    ov = bbox_overlaps_cuda(torch.from_numpy(good).cuda(), torch.from_numpy(gt_boxes.astype(np.float64)).cuda())
-    max_overlaps, anchor_to_gtbox = ov.max(1)
-    gt_max = ov.max(0)[0]
-    is_gt_argmax = (ov == gt_max[None]).any(1)
-    labels = torch.full((ov.size(0),), -1, dtype=torch.long, device=ov.device)
-    labels[max_overlaps < RPN_NEGATIVE_OVERLAP] = 0
-    labels[is_gt_argmax] = 1
-    labels[max_overlaps >= RPN_POSITIVE_OVERLAP] = 1
-    # numpy's argmax takes the FIRST maximum; torch.max on CUDA does not promise that, so re-derive it
-    first_arg = (ov == max_overlaps[:, None]).to(torch.uint8).argmax(1)
+    labels, anchor_to_gtbox, _ = anchor_labels_device(torch.from_numpy(good).cuda(),
+                                                      torch.from_numpy(gt_boxes.astype(np.float64)).cuda())
     labels = labels.cpu().numpy()
-    anchor_to_gtbox = first_arg.cpu().numpy()
+    anchor_to_gtbox = anchor_to_gtbox.cpu().numpy().astype(np.int64)
 
     num_fg = int(RPN_FG_FRACTION * RPN_BATCHSIZE)
     fg_inds = np.where(labels == 1)[0]

@@ -95,7 +95,10 @@ class _HighwayLayerFunction(Function):
                 hp, g5 = h[2:].reshape((T - 1) * B, H), dG2[:(T - 1) * B, :5 * H]
             if hp.size(0) > 0:
                 tgt = tc_ops.direct_grad_target(ctx.base, Wh) if ctx.base is not None else None
-                dWh = tc_ops.gemm(tc_ops.split_transposed(hp), tc_ops.split_transposed(g5), out=tgt)
+                if tc_ops.GEMM_MN:      # Hprev^T dG straight from the row-major buffers (csrc/gemm_mn.cu)
+                    dWh = tc_ops.gemm_mn(tc_ops.split_rows(hp), tc_ops.split_rows(g5), out=tgt)
+                else:
+                    dWh = tc_ops.gemm(tc_ops.split_transposed(hp), tc_ops.split_transposed(g5), out=tgt)
                 if tgt is not None:
                     dWh = None
             else:

@@ -9,8 +9,6 @@ What runs where (B200 path): VGG16 conv1_1..conv5_3 on the tcgen05 implicit-GEMM
 kernel; fc6/fc7/score_fc/bbox_fc and the RPN 1x1 conv on the tcgen05 GEMM; box decode fused
 (csrc/boxes.cu); RPN proposal NMS and the per-class detection NMS each as ONE segmented
 on-device launch pair (csrc/nms.cu) instead of <=150 host round trips per image (:445-452)."""
-import os
-
 import numpy as np
 import torch
 import torch.nn as nn
@@ -114,11 +112,6 @@ class ObjectDetector(nn.Module):
         super().__init__()
         if mode not in self.MODES:
             raise ValueError("invalid mode")
-        if use_resnet and os.environ.get("MOTIFS_EXPERIMENTAL_RESNET", "0") != "1":
-            raise NotImplementedError("ResNet-101 backbone (BASELINE config 3): the layer walk (lib/resnet_tc.py) is "
-                                      "pinned on the CPU but has not run on a B200 yet — set "
-                                      "MOTIFS_EXPERIMENTAL_RESNET=1 to use it. The reference's "
-                                      "RelModel(use_resnet=True) is itself broken (SURVEY.md §8a a1')")
         self.mode = mode
         self.classes = classes
         self.num_gpus = num_gpus
@@ -145,6 +138,7 @@ class ObjectDetector(nn.Module):
         self.dropout_masks = None     # {"roi_fmap.2": mask, "roi_fmap.5": mask} for parity runs
         self._fmap_nhwc = None
         self._fmap_split = None
+        tc_ops.install_load_hook(self)
 
     @property
     def num_classes(self):
@@ -157,10 +151,9 @@ class ObjectDetector(nn.Module):
         """[B,3,S,S] -> stride-16 map [B,512,S/16,S/16] (object_detector.py:110-127). The map lives in
         NHWC; the returned tensor is its NCHW view (same memory)."""
         if any(p.requires_grad for p in self.features.parameters()) and torch.is_grad_enabled():
-            if self.use_resnet or os.environ.get("MOTIFS_EXPERIMENTAL_DETECTOR_TRAIN", "0") != "1":
-                raise NotImplementedError("backbone training (models/train_detector.py, SURVEY.md §8f f1): the "
-                                          "gradient path (lib/conv_tc.py) is pinned on the CPU but has not run on a "
-                                          "B200 yet — set MOTIFS_EXPERIMENTAL_DETECTOR_TRAIN=1 to use it (VGG only)")
+            if self.use_resnet:
+                raise NotImplementedError("training the ResNet-101 backbone: only the VGG gradient path exists "
+                                          "(lib/conv_tc.py); freeze `features` (models/train_rels.py:51-52 does)")
             from lib import conv_tc
             nhwc = conv_tc.vgg_features_train(x.contiguous().float(), self._convs(), tc_ops.VGG16_CFG)
             self._fmap_nhwc, self._fmap_split = None, None       # consumers take the autograd paths
@@ -427,9 +420,6 @@ class RPNHead(nn.Module):
         if torch.is_grad_enabled() and (fmap.requires_grad or c0.weight.requires_grad):
             # training the head (models/train_detector.py): the forward-only kernel call below would silently drop
             # the gradients of conv[0] and of the feature map
-            if os.environ.get("MOTIFS_EXPERIMENTAL_DETECTOR_TRAIN", "0") != "1":
-                raise NotImplementedError("RPN head training (SURVEY.md §8f f1) needs the experimental gradient path: "
-                                          "set MOTIFS_EXPERIMENTAL_DETECTOR_TRAIN=1 (lib/conv_tc.py)")
             from lib import conv_tc
             y = conv_tc.conv3x3(fmap.permute(0, 2, 3, 1).contiguous(), c0.weight, c0.bias, relu=True).clamp(max=6.0)
             c1 = self.conv[2]

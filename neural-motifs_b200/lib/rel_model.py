@@ -276,6 +276,7 @@ class RelModel(nn.Module):
         if self.use_bias:
             self.freq_bias = FrequencyBias(num_objs=self.num_classes, num_rels=self.num_rels)
         self.dropout_masks = None   # {"roi_fmap_obj.2", "roi_fmap_obj.5", "roi_fmap.1.2"} for parity runs
+        tc_ops.install_load_hook(self)   # load_state_dict copies in place: cached bf16 splits are stale afterwards
 
     @property
     def num_classes(self):

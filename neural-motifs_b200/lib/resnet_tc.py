@@ -2,9 +2,9 @@
 `ObjectDetector.feature_map` of the reference, lib/object_detector.py:119-127, over torchvision's
 `resnet101` modules (`load_resnet`, :615-620) — walked layer by layer on this library's kernels.
 
-STATUS: experimental (SURVEY.md §8a row a1'): the graph walk below is pinned on the CPU against torchvision's
-own forward through a test backend (tests/test_resnet_walk.py); the kernel backend has not yet run on a B200,
-so `ObjectDetector(use_resnet=True)` stays behind MOTIFS_EXPERIMENTAL_RESNET=1.
+STATUS (SURVEY.md §8a row a1'): the graph walk below is pinned on the CPU against torchvision's own forward through a
+test backend (tests/test_resnet_walk.py); the kernel backend is held to fp64 and to the oracle's detector on a B200 by
+tests/test_resnet_gpu.py (green since round 2).
 
 Layout: activations are NHWC fp32 [B,H,W,C] between operations. A backend supplies five operations:
     stem(x_nchw, conv)            7x7 / stride 2 / pad 3, 3 -> 64

@@ -6,6 +6,8 @@ The arithmetic replaced is nn.Linear / nn.Conv2d of the reference (cuBLAS / cuDN
 fc6/fc7 `lib/object_detector.py:129-138`, `lib/rel_model.py:360-374,439-448`, post_lstm /
 rel_compress `lib/rel_model.py:377,390,503,524`, VGG16 features `lib/object_detector.py:110-127`.
 """
+import weakref
+
 import torch
 from torch.autograd import Function
 
@@ -110,11 +112,15 @@ def gemm(A, B, bias=None, relu=False, want_f32=True, want_split=False, out=None)
     return C if want_f32 else Cs
 
 
-GEMM_MN = __import__("os").environ.get("MOTIFS_GEMM_MN", "0") == "1"   # experimental csrc/gemm_mn.cu for weight gradients
+# Weight gradients dW = dY^T X run on the MN-major kernel (csrc/gemm_mn.cu) straight from the row-major (hi, lo) pairs —
+# dY split ONCE per backward (shared with dX = dY W), X's split kept from forward — instead of two transposing split
+# passes per layer (round 1: split_transpose_kernel 1.04 ms + part of split_kernel's 0.84 ms per step).
+# MOTIFS_GEMM_MN=0 restores the K-major route (A/B runs).
+GEMM_MN = __import__("os").environ.get("MOTIFS_GEMM_MN", "1") == "1"
 
 
 def gemm_mn(At, Bt, out=None):
-    """EXPERIMENTAL. C[M,N] = At^T @ Bt with At a SplitMat of [K, M] (rows = the reduction index) and Bt of [K, N]:
+    """C[M,N] = At^T @ Bt with At a SplitMat of [K, M] (rows = the reduction index) and Bt of [K, N]:
     the weight-gradient product dW = dY^T X straight from the row-major activations (csrc/gemm_mn.cu)."""
     assert At.rows == Bt.rows, (At.rows, Bt.rows)
     K, M, N = At.rows, At.K, Bt.K
@@ -137,8 +143,12 @@ def gemm_mn(At, Bt, out=None):
 
 
 # ------------------------------------------------------------------ weight split cache
+# key (id(param), kind) -> (weakref to the parameter, version tuple, value). The entry dies with the parameter
+# (weakref callback), so a new model whose parameters reuse a dead model's id() / caching-allocator address
+# can never hit the dead model's splits, and rebuilt models do not leak their fc6 splits (0.8 GB each).
 _cache = {}
 WEIGHT_EPOCH = 0     # bumped by optimizers that update parameters through raw pointers (lib/fused_optim.py)
+LOAD_EPOCH = 0       # bumped by load_state_dict hooks and by invalidate_all(): applies to frozen parameters too
 
 
 def bump_weight_epoch():
@@ -146,30 +156,50 @@ def bump_weight_epoch():
     WEIGHT_EPOCH += 1
 
 
+def invalidate_all():
+    """Every cached split is stale from now on (trainable AND frozen parameters). `load_state_dict` of RelModel /
+    ObjectDetector calls this through a post hook. A raw `param.data.copy_(...)` AFTER a forward changes neither
+    `_version` nor `data_ptr` (the checkpoint idiom of models/train_rels.py:86-95 runs before the first forward and
+    is safe): callers that write `.data` later must call this (or clear_cache())."""
+    global LOAD_EPOCH
+    LOAD_EPOCH += 1
+
+
+def install_load_hook(module):
+    """load_state_dict on `module` invalidates the split cache (state-dict loads copy in place)."""
+    module.register_load_state_dict_post_hook(lambda mod, incompatible: invalidate_all())
+
+
+def _lookup(owner, key, ver, maker, src):
+    hit = _cache.get(key)
+    if hit is not None and hit[0]() is owner and hit[1] == ver:
+        return hit[2]
+    val = maker(src.detach())
+
+    def _evict(ref, key=key):
+        cur = _cache.get(key)
+        if cur is not None and cur[0] is ref:
+            del _cache[key]
+    _cache[key] = (weakref.ref(owner, _evict), ver, val)
+    return val
+
+
+def _version_of(t, shape):
+    return (t.data_ptr(), t._version, tuple(shape), WEIGHT_EPOCH if t.requires_grad else 0, LOAD_EPOCH)
+
 
 def _cached(param, kind, maker):
-    """Split copies of a parameter are rebuilt only when the parameter changes (optimizer steps
-    bump `_version`); frozen weights are split once."""
-    key = (id(param), kind)
-    ver = (param.data_ptr(), param._version, tuple(param.shape), WEIGHT_EPOCH if param.requires_grad else 0)
-    hit = _cache.get(key)
-    if hit is not None and hit[0] == ver:
-        return hit[1]
-    val = maker(param.detach())
-    _cache[key] = (ver, val)
-    return val
+    """Split copies of a parameter are rebuilt only when the parameter changes (optimizer steps bump `_version`
+    or the weight epoch); frozen weights are split once per load."""
+    owner = param._base if param._base is not None else param     # views (w.view(out, -1)) are temporaries: key on the base
+    key = (id(owner), kind) if owner is param else \
+        (id(owner), kind, param.storage_offset(), tuple(param.shape), tuple(param.stride()))
+    return _lookup(owner, key, _version_of(owner, param.shape), maker, param)
 
 
 def _cached_view(base, tag, view, maker):
     """Like _cached, for a view (slice) of the flat parameter `base`; `tag` names the slice."""
-    key = (id(base), tag)
-    ver = (base.data_ptr(), base._version, tuple(view.shape), WEIGHT_EPOCH if base.requires_grad else 0)
-    hit = _cache.get(key)
-    if hit is not None and hit[0] == ver:
-        return hit[1]
-    val = maker(view.detach())
-    _cache[key] = (ver, val)
-    return val
+    return _lookup(base, (id(base), tag), _version_of(base, view.shape), maker, view)
 
 
 def weight_split(weight):          # [N,K] -> B operand of  x @ W^T
@@ -235,21 +265,29 @@ class _LinearTC(Function):
     def forward(ctx, x, weight, bias):
         xs = split_rows(x.detach())
         y = gemm(xs, weight_split(weight), bias=bias.detach() if bias is not None else None)
-        ctx.save_for_backward(x, weight)
         ctx.has_bias = bias is not None
+        if GEMM_MN:         # keep the bf16 pair of x (same bytes as x): it is the B operand of the weight-gradient GEMM
+            ctx.save_for_backward(weight, xs.hi, xs.lo)
+            ctx.xdims = (xs.rows, xs.K, xs.Kp)
+        else:
+            ctx.save_for_backward(weight, x)
         return y
 
     @staticmethod
     def backward(ctx, gy):
-        x, weight = ctx.saved_tensors
         gy = gy.contiguous()
         gx = gw = gb = None
+        gys = split_rows(gy) if (ctx.needs_input_grad[0] or (GEMM_MN and ctx.needs_input_grad[1])) else None
+        if GEMM_MN:
+            weight, xhi, xlo = ctx.saved_tensors
+        else:
+            weight, x = ctx.saved_tensors
         if ctx.needs_input_grad[0]:
-            gx = gemm(split_rows(gy), weight_split_t(weight))                 # [M,N] x [K,N]^T -> [M,K]
+            gx = gemm(gys, weight_split_t(weight))                              # [M,N] x [K,N]^T -> [M,K]
         if ctx.needs_input_grad[1]:
             tgt = direct_grad_target(weight)
-            if GEMM_MN:     # experimental: no transposed operand copies (csrc/gemm_mn.cu)
-                gw = gemm_mn(split_rows(gy), split_rows(x.detach()), out=tgt)
+            if GEMM_MN:
+                gw = gemm_mn(gys, SplitMat(xhi, xlo, *ctx.xdims), out=tgt)        # dY^T X, no transposed copies
             else:
                 gw = gemm(split_transposed(gy), split_transposed(x.detach()), out=tgt) # [N,M] x [K,M]^T -> [N,K]
             if tgt is not None:
@@ -265,21 +303,33 @@ class _MatmulTC(Function):
 
     @staticmethod
     def forward(ctx, x, w, base, tag):
-        y = gemm(split_rows(x.detach()), _cached_view(base, (tag, "T"), w, split_transposed))
-        ctx.save_for_backward(x, w)
+        xs = split_rows(x.detach())
+        y = gemm(xs, _cached_view(base, (tag, "T"), w, split_transposed))
+        if GEMM_MN:
+            ctx.save_for_backward(w, xs.hi, xs.lo)
+            ctx.xdims = (xs.rows, xs.K, xs.Kp)
+        else:
+            ctx.save_for_backward(w, x)
         ctx.base, ctx.tag = base, tag
         return y
 
     @staticmethod
     def backward(ctx, gy):
-        x, w = ctx.saved_tensors
         gy = gy.contiguous()
         gx = gw = None
+        gys = split_rows(gy) if (ctx.needs_input_grad[0] or (GEMM_MN and ctx.needs_input_grad[1])) else None
+        if GEMM_MN:
+            w, xhi, xlo = ctx.saved_tensors
+        else:
+            w, x = ctx.saved_tensors
         if ctx.needs_input_grad[0]:
-            gx = gemm(split_rows(gy), _cached_view(ctx.base, (ctx.tag, "R"), w, split_rows))   # gy @ w^T
+            gx = gemm(gys, _cached_view(ctx.base, (ctx.tag, "R"), w, split_rows))   # gy @ w^T
         if ctx.needs_input_grad[1]:
             tgt = direct_grad_target(ctx.base, w)
-            gw = gemm(split_transposed(x.detach()), split_transposed(gy), out=tgt)             # x^T @ gy
+            if GEMM_MN:
+                gw = gemm_mn(SplitMat(xhi, xlo, *ctx.xdims), gys, out=tgt)         # x^T @ gy
+            else:
+                gw = gemm(split_transposed(x.detach()), split_transposed(gy), out=tgt)
             if tgt is not None:
                 gw = None          # written into the slice of base.grad that belongs to this view
         return gx, gw, None, None

@@ -5,7 +5,7 @@ architecture, or a call fails, an exception is raised.  Nothing here imports `or
 """
 import ctypes
 import os
-from ctypes import c_int, c_float, c_void_p, c_longlong, c_size_t, c_char_p
+from ctypes import c_int, c_float, c_double, c_void_p, c_longlong, c_size_t, c_char_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libmotifs_b200.so")
@@ -63,6 +63,9 @@ SIGNATURES = {
     "mb200_gemm_bf16x3_mn": (c_int, [P, P, c_longlong, P, P, c_longlong, c_int, c_int, c_int, P, c_longlong, P, P]),
     "mb200_sumsq_accum": (c_int, [P, c_longlong, P, P]),
     "mb200_sgd_momentum_clip": (c_int, [P, P, P, c_longlong, c_float, c_float, c_float, P, c_float, c_int, c_int, P]),
+    "mb200_sgd_momentum_clip_scaled": (c_int, [P, P, P, c_longlong, c_float, c_float, c_float, P, c_float, c_float, c_int, c_int, P]),
+    "mb200_anchor_targets": (c_int, [P, c_int, P, c_int, c_double, c_double, P, P, P, P, P]),
+    "mb200_gemm_set_pair_mode": (c_int, [c_int]),
     "mb200_sgemm": (c_int, [c_int, c_int, c_int, c_int, c_int, c_float, P, c_int, P, c_int, c_float, P, c_int, P]),
 }
 

@@ -1,14 +1,12 @@
-"""GPU check of the EXPERIMENTAL MN-major bf16x3 GEMM (csrc/gemm_mn.cu): weight-gradient products dW = dY^T X consumed
-straight from row-major activations, no transposed operand copies. Written at the end of round 1 without GPU budget
-left, hence gated: set MOTIFS_GEMM_MN=1 (the same flag switches `linear_tc`'s backward to it)."""
+"""GPU check of the MN-major bf16x3 GEMM (csrc/gemm_mn.cu): weight-gradient products dW = dY^T X consumed straight from
+row-major activations, no transposed operand copies. It is what `linear_tc` / `matmul_tc` / the LSTM and mask-branch
+weight gradients run on (lib/tc_ops.py)."""
 import os
 
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("MOTIFS_GEMM_MN", "0") != "1",
-                                 reason="experimental MN-major GEMM: set MOTIFS_GEMM_MN=1")]
+pytestmark = pytest.mark.gpu
 
 
 def relerr(a, b):

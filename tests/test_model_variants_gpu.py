@@ -12,9 +12,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("MOTIFS_VARIANTS_GPU", "0") != "1",
-                                 reason="not yet run on a B200: set MOTIFS_VARIANTS_GPU=1")]
+pytestmark = pytest.mark.gpu
 
 SCRIPT = dict(hidden_dim=512, pooling_dim=4096, nl_obj=2, nl_edge=4, order='leftright', use_bias=True, use_tanh=False,
               limit_vision=False)

@@ -362,3 +362,46 @@ def test_maxpool3s2_matches_torch(cuda):
         g = torch.randn_like(ref)
         y.backward(g); ref.backward(g)
         assert torch.equal(x.grad, ref_in.grad)
+
+
+# ------------------------------------------------------------------------------- RPN anchor targets (a13)
+def test_anchor_target_layer_matches_reference_fixture(cuda, golden):
+    """lib/fpn/anchor_targets.py:16-105 on the warp-per-anchor kernels vs the REFERENCE's own function run with the same
+    numpy RNG state (tests/golden/make_golden.py): anchors, (h, w, A) indices, box targets and labels identical."""
+    from lib.fpn.anchor_targets import anchor_target_layer
+    np.random.seed(7)
+    anchors, inds, targets, labels = anchor_target_layer(golden["at_gt"], (592, 592))
+    assert np.array_equal(anchors, golden["at_anchors"])
+    assert np.array_equal(inds, golden["at_inds"])
+    assert np.array_equal(targets, golden["at_targets"])
+    assert np.array_equal(labels, golden["at_labels"])
+
+
+@pytest.mark.parametrize("G", [1, 7, 40, 97])
+def test_anchor_labels_device_vs_oracle(cuda, G):
+    """Labels before subsampling, first arg-max and max overlap vs the oracle (numpy float64) for GT counts that span
+    one lane stride to several, including a GT box outside every anchor (its column maximum is 0: every anchor with a zero
+    overlap 'attains' it, as in the reference, anchor_targets.py:57-58)."""
+    from lib.fpn.anchor_targets import anchor_labels_device
+    from oracle import host, ops
+    rng = np.random.RandomState(G)
+    ans = host.generate_anchors().reshape(-1, 4)
+    inside = np.where((ans[:, 0] >= 0) & (ans[:, 1] >= 0) & (ans[:, 2] < 592) & (ans[:, 3] < 592))[0]
+    good = ans[inside]
+    x1 = rng.uniform(0, 450, G); y1 = rng.uniform(0, 450, G)
+    gt = np.stack([x1, y1, np.minimum(x1 + rng.uniform(16, 300, G), 591), np.minimum(y1 + rng.uniform(16, 300, G), 591)], 1)
+    gt = gt.astype(np.float32).astype(np.float64)
+    if G >= 7:
+        gt[3] = [5000, 5000, 5100, 5100]
+        gt[5] = gt[2]                                  # duplicate GT box: arg-max must be the FIRST of the two
+    labels, arg, mx = anchor_labels_device(torch.from_numpy(good).to(cuda), torch.from_numpy(gt).to(cuda))
+    ov = ops.bbox_overlaps_f64(good, gt)
+    want_arg = ov.argmax(1)
+    want_mx = ov[np.arange(len(good)), want_arg]
+    want = -np.ones(len(good), dtype=np.int64)
+    want[want_mx < 0.3] = 0
+    want[np.where(ov == ov.max(0)[None])[0]] = 1
+    want[want_mx >= 0.7] = 1
+    assert np.array_equal(mx.cpu().numpy(), want_mx)
+    assert np.array_equal(arg.cpu().numpy(), want_arg)
+    assert np.array_equal(labels.cpu().numpy(), want)

@@ -1,7 +1,8 @@
 """The PRODUCT on the GPU against the outputs of the REFERENCE's own RelModel (tests/golden/reference_model_eval.npz,
 produced by tests/golden/make_golden_model.py; see tests/test_reference_model_pin.py for what ran there). Written at
-the end of round 1 without GPU budget left to run it, hence gated: set MOTIFS_REFERENCE_PIN_GPU=1. (The ungated chain
-is reference -> oracle on the CPU, oracle -> product in tests/test_model_gpu.py.)"""
+the end of round 1; first run in round 2, where it exposed an ILL-CONDITIONED fixture state (BatchNorm running statistics of
+the position embedding that do not normalise pixel coordinates -> saturated, chaotic highway LSTMs: CPU fp32 vs fp64 of
+the reference recurrence differed by 1.3 %), fixed in tests/golden/synthetic_state.py and the fixtures regenerated."""
 import os
 import sys
 
@@ -12,9 +13,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("MOTIFS_REFERENCE_PIN_GPU", "0") != "1",
-                                 reason="not yet run on a B200: set MOTIFS_REFERENCE_PIN_GPU=1")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("mode", ["predcls", "sgcls"])

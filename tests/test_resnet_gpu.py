@@ -1,7 +1,6 @@
-"""GPU checks of the experimental ResNet-101 C4 path (SURVEY.md §8a row a1', lib/resnet_tc.py). They run only with
-MOTIFS_EXPERIMENTAL_RESNET=1: the kernel backend of the layer walk has not been on a B200 yet (round 1 ran out of
-GPU budget after the CPU pin of the walk, tests/test_resnet_walk.py); round 2 enables them, fixes what they find and
-removes the gate."""
+"""GPU checks of the ResNet-101 C4 path (SURVEY.md §8a row a1', lib/resnet_tc.py): the kernel backend of the layer walk
+(pinned on the CPU against torchvision by tests/test_resnet_walk.py) against fp64 and against the oracle's detector.
+First run on a B200 in round 2 (all green); the round-1 environment gate is gone."""
 import os
 
 import numpy as np
@@ -9,9 +8,7 @@ import pytest
 import torch
 import torch.nn.functional as F
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("MOTIFS_EXPERIMENTAL_RESNET", "0") != "1",
-                                 reason="experimental ResNet path: set MOTIFS_EXPERIMENTAL_RESNET=1")]
+pytestmark = pytest.mark.gpu
 
 
 def relerr(a, b):
