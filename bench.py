@@ -128,16 +128,26 @@ def get_optim(model, lr):
     from lib.fused_optim import FlatSGD
     fc = [p for n, p in model.named_parameters() if n.startswith('roi_fmap') and p.requires_grad]
     non_fc = [p for n, p in model.named_parameters() if not n.startswith('roi_fmap') and p.requires_grad]
-    return FlatSGD([(fc, lr / 10.0), (non_fc, lr)], momentum=0.9, weight_decay=1e-4, max_norm=5.0)
+    # defer_step: the gradient all-reduce + the fused clip/SGD kernel run on a side stream underneath the NEXT step's
+    # frozen backbone; RelModel.forward joins the streams before it reads the first trainable parameter.
+    return FlatSGD([(fc, lr / 10.0), (non_fc, lr)], momentum=0.9, weight_decay=1e-4, max_norm=5.0, defer_step=True)
 
 
 def train_step(model, optimizer, reducer=None, fwd_tuple=None, blob=None):
     """models/train_rels.py:118-152 (train_batch): forward, two cross-entropies, backward, clip 5, step.
     The data-parallel gradient average is one all-reduce per flat gradient buffer."""
     from torch.nn import functional as F
+    import torch.distributed as dist
     result = model[blob] if blob is not None else model(*fwd_tuple)
-    loss = F.cross_entropy(result.rm_obj_dists, result.rm_obj_labels) + \
-        F.cross_entropy(result.rel_dists, result.rel_labels[:, -1])
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        # the reference averages over the objects / relations of ALL GPUs (gather_res, then one mean): count-weighted
+        from lib.data_parallel import count_weighted_loss
+        loss = count_weighted_loss([
+            (F.cross_entropy(result.rm_obj_dists, result.rm_obj_labels, reduction='sum'), result.rm_obj_labels.size(0)),
+            (F.cross_entropy(result.rel_dists, result.rel_labels[:, -1], reduction='sum'), result.rel_labels.size(0))])
+    else:
+        loss = F.cross_entropy(result.rm_obj_dists, result.rm_obj_labels) + \
+            F.cross_entropy(result.rel_dists, result.rel_labels[:, -1])
     optimizer.zero_grad()
     loss.backward()
     optimizer.all_reduce_grads()
@@ -173,12 +183,19 @@ def run_b200(args):
     import torch
     import torch.distributed as dist
     import motifs_cabi
-    from lib import tc_ops
+    from lib import fused_optim, tc_ops
     from lib.data_parallel import init_from_env
     from dataloaders.synthetic import make_numpy_batch, SyntheticBlob
 
-    if "MOTIFS_KEEP_NCCL_DEBUG" not in os.environ:
-        os.environ["NCCL_DEBUG"] = "WARN"          # NCCL's version banner would otherwise land on stdout before the JSON line
+    # NCCL prints its INFO lines (version banner, "comm ... rank r nranks N ... Init COMPLETE") on STDOUT; the contract
+    # wants exactly one JSON line there. Keep the lines (they are the evidence of the communicator's size) but move
+    # everything that is not the JSON line to stderr: fd 1 is pointed at fd 2 for the run, the JSON line is written to
+    # the saved original stdout at the end.
+    os.environ.setdefault("NCCL_DEBUG", "INFO")
+    os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     rank, world, local = init_from_env("nccl")
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py (impl b200) needs a CUDA device; there is no CPU fallback")
@@ -208,6 +225,7 @@ def run_b200(args):
         for i in range(steps):
             fn(i)
             ev = torch.cuda.Event(enable_timing=True); ev.record(); marks.append(ev)
+        fused_optim.wait_pending_updates()      # the last step's deferred update belongs to the timed region
         e1.record()
         barrier()
         per_step = [a.elapsed_time(b) for a, b in zip([e0] + marks[:-1], marks)]
@@ -247,6 +265,11 @@ def run_b200(args):
             gc_log.append((info.get("generation"), round((time.perf_counter() - gc_t0[0]) * 1e3, 2)))
     gc.callbacks.append(gc_cb)
     gc.collect(); gc.freeze(); gc.disable()
+    # the collection just released cyclic garbage that held device buffers: two more untimed steps let the caching
+    # allocator settle again (round 2: one 700 MB cudaMalloc — 58 ms — landed in the first timed step otherwise)
+    for i in range(2):
+        train_step(model, opt, reducer, fwd_tuple=resident[i % len(resident)])
+    W += 2
     mem0 = torch.cuda.memory_stats(dev)
     calls0 = motifs_cabi.LAUNCHER_CALLS
     ms_res = timed(lambda i: train_step(model, opt, reducer, fwd_tuple=resident[i % len(resident)]), args.steps)
@@ -287,6 +310,7 @@ def run_b200(args):
         dist.destroy_process_group()
     if rank != 0:
         return
+    lstm_mb = lstm_microbench(dev) if world == 1 else None
     imgs = BATCH_PER_GPU * world * args.steps
     value = imgs / (ms_res * 1e-3)
     out = {
@@ -312,7 +336,9 @@ def run_b200(args):
                      "backbone_conv_tflops": (sum(f for f, _ in conv) / (sum(t for _, t in conv) * 1e-3) / 1e12) if conv else None,
                      "note": "algorithmic fp32-equivalent FLOPs; the bf16x3 scheme issues 3 tensor-core MACs per "
                              "algorithmic MAC, so tensor-pipe busy fraction is ~3x frac",
-                     "traffic": traffic_from_profile()},
+                     "traffic": None,
+                     "traffic_note": "not measured inside this run (needs ncu); per-launch dram__bytes of one step vs the "
+                                     "algorithmic bytes: profiles/r02_gemm_traffic.json"},
         "clocks": clocks,
         "host": host_notes,
         "step_ms": {"value_leg": [round(t, 2) for t in steps_res], "e2e_leg": [round(t, 2) for t in timed.last_per_step]},
@@ -320,20 +346,57 @@ def run_b200(args):
     }
     if world == 1:
         out["roi_align"] = roi_align_microbench(dev, pk, kind)
+        out["lstm"] = lstm_mb
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(sample_images=2)
-    print(json.dumps(out), flush=True)
+    sys.stdout.flush()
+    os.write(real_stdout, (json.dumps(out) + "\n").encode())
 
 
-def traffic_from_profile():
-    """DRAM bytes per gemm_bf16x3_kernel launch (dram__bytes_read.sum + dram__bytes_write.sum averaged over
-    the launches of one training step) from the committed ncu capture under profiles/; None if absent."""
-    path = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
-    try:
-        with open(path) as f:
-            return float(json.load(f)["traffic_per_launch_bytes"])
-    except (OSError, KeyError, ValueError):
-        return None
+def lstm_microbench(dev):
+    """BASELINE.json metric (iv) / configs[4]: AlternatingHighwayLSTM, H=512, 2 layers (forward, backward), B=256,
+    T in {32, 64, 128, 256}, inputs 712 (edge context) and 4424 (object context), all lengths = T. Forward in eval mode
+    and forward+backward in training mode, median of 5 after 2 warm-ups, CUDA events. FLOPs:
+    sum_l T * (2*B*In_l*6H + 2*B*H*5H). The reference kernels' times beside these: profiles/ (tools/microbench_ops.py)."""
+    import numpy as np
+    import torch
+    from torch.nn.utils.rnn import pack_padded_sequence
+    from lib.lstm.highway_lstm_cuda.alternating_highway_lstm import AlternatingHighwayLSTM
+    H, L, B = 512, 2, 256
+    rows = []
+    for In in (712, 4424):
+        torch.manual_seed(0)
+        m = AlternatingHighwayLSTM(In, H, L, recurrent_dropout_probability=0.1).to(dev)
+        for T in (32, 64, 128, 256):
+            x = torch.randn(T, B, In, device=dev)
+            packed = pack_padded_sequence(x, [T] * B)
+            flops = sum(T * (2.0 * B * (In if l == 0 else H) * 6 * H + 2.0 * B * H * 5 * H) for l in range(L))
+
+            def fwd():
+                with torch.no_grad():
+                    m.eval()
+                    m(packed)
+
+            def fwd_bwd():
+                m.train()
+                xr = x.detach().requires_grad_(True)
+                out, _ = m(pack_padded_sequence(xr, [T] * B))
+                out.data.sum().backward()
+                m.weight.grad = None; m.bias.grad = None
+
+            def t(fn):
+                ts = []
+                for i in range(7):
+                    a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+                    a.record(); fn(); b.record(); torch.cuda.synchronize()
+                    if i >= 2:
+                        ts.append(a.elapsed_time(b))
+                return float(np.median(ts))
+            f_ms, fb_ms = t(fwd), t(fwd_bwd)
+            rows.append({"In": In, "T": T, "fwd_ms": f_ms, "fwd_tflops": flops / f_ms / 1e9,
+                         "fwd_bwd_ms": fb_ms, "gflop_fwd": flops / 1e9})
+        del m
+    return {"config": "AlternatingHighwayLSTM H=512, L=2, B=256, all lengths = T (BASELINE configs[4])", "rows": rows}
 
 
 def roi_align_microbench(dev, pk, kind):
@@ -420,33 +483,33 @@ def oracle_step_time(B, reps=1, threads=None, warm=1):
 
 
 def cpu_baseline(sample_images=2):
-    sec, cores = oracle_step_time(sample_images, reps=1)
+    sec, cores = oracle_step_time(sample_images, reps=3)
     return {"value": sample_images / sec, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": "1 timed SGCls train step (after 1 untimed) of the oracle port on a %d-image batch of the same "
+            "sample": "mean of 3 timed SGCls train steps (after 1 untimed) of the oracle port on a %d-image batch of the same "
                       "per-image shape (20 boxes, 256 rel triples / image); the reference has no CPU path and "
                       "PyTorch 0.3 is not installable here (SURVEY.md section 8c)" % sample_images,
             "seconds_per_step": sec}
 
 
 def run_reference(args):
+    """CPU arm: the oracle port (the reference has no CPU path and PyTorch 0.3 is not installable)
+    stepping the SAME workload as the b200 arm — one SGCls train step on a 6-image batch per step, all host threads."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    B = 1
+    B = BATCH_PER_GPU
     W = max(args.warmup, 1)
-    # each "step" is a bounded sample: one oracle training step on a 1-image batch
-    import torch
     sec, cores = oracle_step_time(B, reps=args.steps, warm=W)
     value = B / sec
     out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
            "warmup": W, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f32", "data": "synthetic",
-           "config": {"workload": "MotifNet SGCls train_rels.py step, VGG16 backbone, 592x592 synthetic images, 20 GT boxes + "
-                                  "15 GT rels per image; CPU arm steps over a 1-image sample of the per-GPU batch of 6",
+           "config": {"workload": "MotifNet SGCls train_rels.py step, VGG16 backbone, batch 6x592x592 per GPU, "
+                                  "20 GT boxes + 15 GT rels per image (1536 rel triples), fwd+bwd+clip+SGD",
                       "global_batch": B, "parallelism": "cpu"},
            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                            "sample": "oracle port (oracle/model.py, torch fp32 CPU, all host threads), 1-image batch per "
-                                      "step; averaged over %d steps after %d warm-up" % (args.steps, W)},
+                            "sample": "oracle port (oracle/model.py, torch fp32 CPU, all host threads), the full 6-image batch "
+                                      "per step; mean over %d steps after %d warm-up" % (args.steps, W)},
            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out), flush=True)
 

@@ -101,6 +101,11 @@ int mb200_bbox_overlaps_f64(const double* boxes, int N, const double* query, int
 int mb200_anchor_targets(const double* anchors, int N, const double* gt_boxes, int G, double neg_thr, double pos_thr,
                          unsigned long long* gt_max_ws, double* max_overlaps, int* argmax, long long* labels,
                          cudaStream_t stream);
+/* replaces the host loop of lib/lstm/decoder_rnn.py:230-247 (overlap-aware greedy label commitment in SGDet eval):
+ * boxes DEV [N,C,4] (class-specific boxes of the detections), probs DEV [N,C] (softmax), thresh = nms_thresh (0.3);
+ * commit DEV [N] int64. Returns MB200_ERR_UNSUPPORTED when N*C*4 bytes exceed 200 KB of shared memory. */
+int mb200_decoder_commit(const float* boxes, const float* probs, int N, int C, float thresh, long long* commit,
+                         cudaStream_t stream);
 /* replaces lib/get_union_boxes.py:82-87 (union roi) and the pair gather of :47. */
 int mb200_union_rois(const float* rois, const long long* pairs, int num_pairs, float* union_rois,
                      float* pair_boxes, cudaStream_t stream);
@@ -225,6 +230,8 @@ int mb200_gemm_bf16x3_mn(const void* Ahi, const void* Alo, long long lda, const 
 /* tcgen05 GEMM / conv kernel selection: 0 = 1-CTA kernels only, 1 = per-shape choice (default), 2 = the CTA-pair
  * (cta_group::2, 256-row tiles) kernel whenever the shape allows. Returns the previous mode. Tests and A/B runs. */
 int mb200_gemm_set_pair_mode(int mode);
+/* 3x3 convolution kernel: 0 = tap-by-tap shifted TMA boxes, 1 = per layer (default), 2 = shared-memory halo staging always. */
+int mb200_conv_set_halo_mode(int mode);
 
 /* *acc += sum_i x[i]^2 (double accumulator on the device, caller zeroes it): the global gradient norm of
  * clip_grad_norm (lib/pytorch_misc.py:416-459) as one pass per flat buffer. x 16-byte aligned. */

@@ -213,6 +213,72 @@ __global__ void anchor_label_kernel(const double* __restrict__ anchors, int N, c
   }
 }
 
+
+// ------------------------------------------------------------------ decoder: overlap-aware greedy commitment
+// lib/lstm/decoder_rnn.py:230-247 of the reference — a host numpy loop over the detections there (D2H of the [N,N,C]
+// overlap tensor and of the class probabilities, then N iterations of argmax / suppress). One CTA here: the [N,C]
+// probabilities live in shared memory; every iteration takes the global arg-max (np.argmax order: the FIRST maximum in
+// row-major order), commits that (box, class), zeroes the class for every box whose class-specific box overlaps the
+// winner's by IoU >= thresh (nms_overlaps, lib/fpn/box_utils.py:134-154: separate fp32 ops, no fused multiply-add),
+// and retires the winner's row with -1. boxes [N,C,4], probs [N,C] (softmax; column 0 is cleared here), out [N] int64.
+__global__ void __launch_bounds__(512) decoder_commit_kernel(const float* __restrict__ boxes, const float* __restrict__ probs,
+                                                             int N, int C, float thresh, long long* __restrict__ commit) {
+  extern __shared__ float s_p[];                 // [N*C]
+  __shared__ float s_val[16];
+  __shared__ int s_idx[16];
+  __shared__ int s_win;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int total = N * C;
+  for (int i = tid; i < total; i += blockDim.x) s_p[i] = (i % C == 0) ? 0.f : probs[i];
+  for (int i = tid; i < N; i += blockDim.x) commit[i] = 0;
+  __syncthreads();
+  for (int it = 0; it < N; ++it) {
+    float best = -INFINITY; int bi = 0x7fffffff;
+    for (int i = tid; i < total; i += blockDim.x) {
+      const float v = s_p[i];
+      if (v > best) { best = v; bi = i; }        // ascending i per thread: keeps this thread's first maximum
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    if (lane == 0) { s_val[warp] = best; s_idx[warp] = bi; }
+    __syncthreads();
+    if (warp == 0) {
+      best = lane < (blockDim.x >> 5) ? s_val[lane] : -INFINITY;
+      bi = lane < (blockDim.x >> 5) ? s_idx[lane] : 0x7fffffff;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+      }
+      if (lane == 0) s_win = bi;
+    }
+    __syncthreads();
+    const int b = s_win / C, cls = s_win - b * C;
+    if (tid == 0) commit[b] = cls;
+    const float* wb = boxes + ((size_t)b * C + cls) * 4;
+    const float wx1 = wb[0], wy1 = wb[1], wx2 = wb[2], wy2 = wb[3];
+    const float warea = __fmul_rn(__fadd_rn(__fadd_rn(wx2, -wx1), 1.0f), __fadd_rn(__fadd_rn(wy2, -wy1), 1.0f));
+    for (int j = tid; j < N; j += blockDim.x) {
+      const float* q = boxes + ((size_t)j * C + cls) * 4;
+      // is_overlap[b, j, cls]: inter from min/max of the corners, union = (-inter + area[j]) + area[b]
+      const float iw = fmaxf(__fadd_rn(__fadd_rn(fminf(wx2, q[2]), -fmaxf(wx1, q[0])), 1.0f), 0.f);
+      const float ih = fmaxf(__fadd_rn(__fadd_rn(fminf(wy2, q[3]), -fmaxf(wy1, q[1])), 1.0f), 0.f);
+      const float inter = __fmul_rn(iw, ih);
+      const float qarea = __fmul_rn(__fadd_rn(__fadd_rn(q[2], -q[0]), 1.0f), __fadd_rn(__fadd_rn(q[3], -q[1]), 1.0f));
+      const float uni = __fadd_rn(__fadd_rn(-inter, qarea), warea);
+      if (__fdiv_rn(inter, uni) >= thresh) s_p[j * C + cls] = 0.f;
+    }
+    __syncthreads();
+    for (int c = tid; c < C; c += blockDim.x) s_p[b * C + c] = -1.f;
+    __syncthreads();
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -246,6 +312,22 @@ int mb200_anchor_targets(const double* anchors, int N, const double* gt_boxes, i
   MB200_CHECK_LAUNCH("anchor_rowmax_kernel");
   anchor_label_kernel<<<blocks, 256, 0, stream>>>(anchors, N, gt_boxes, G, max_overlaps, gt_max_ws, neg_thr, pos_thr, labels);
   MB200_CHECK_LAUNCH("anchor_label_kernel");
+  return MB200_OK;
+}
+
+int mb200_decoder_commit(const float* boxes, const float* probs, int N, int C, float thresh, long long* commit,
+                         cudaStream_t stream) {
+  if (N <= 0) return MB200_OK;
+  if (C <= 1) return MB200_ERR_ARG;
+  const size_t smem = (size_t)N * C * sizeof(float);
+  if (smem > 200 * 1024) return MB200_ERR_UNSUPPORTED;        // > ~330 detections x 151 classes: caller keeps the host loop
+  static bool attr = false;
+  if (!attr) {
+    MB200_CHECK(cudaFuncSetAttribute(decoder_commit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr = true;
+  }
+  decoder_commit_kernel<<<1, 512, smem, stream>>>(boxes, probs, N, C, thresh, commit);
+  MB200_CHECK_LAUNCH("decoder_commit_kernel");
   return MB200_OK;
 }
 

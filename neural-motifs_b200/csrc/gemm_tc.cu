@@ -28,7 +28,8 @@ namespace {
 constexpr int BM = 128, BK = 64;
 constexpr int ACC_STAGES = 2;                  // TMEM accumulators: epilogue of tile i overlaps the MMAs of tile i+1
 constexpr int TILE_A = BM * BK * 2;            // 16 KB
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 320;          // warp 0: TMA, warp 1: MMA + TMEM owner, warps 2..9: epilogue (two per TMEM lane quarter)
+constexpr int kEpiThreads = 256;
 constexpr int TH = 8, TW = 16;                 // conv: spatial tile = 128 output pixels
 
 // Two tile shapes. ncu on the 128x128 tile: tensor pipe 34 % with 7.4 TB/s of L2->SM traffic — the
@@ -87,6 +88,107 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
+
+// ------------------------------------------------------------------ epilogue of one 128-row x BN tile (all kernels)
+// ncu (source page, conv1_2): more than half of all warp samples sat in the epilogue — FADDs waiting for the per-element
+// bias LDGs, moves waiting for tcgen05.ld, and a GPU-scope MEMBAR + ERRBAR in front of the release.cluster arrive — with
+// one warp per scheduler nothing hides those latencies, and for short-K tiles the epilogue, not the MMA, set the pace.
+//  * the tile's bias slice is staged in shared memory BEFORE the wait for the accumulator (broadcast LDS afterwards);
+//  * the TMEM read of chunk c+1 is in flight while chunk c is converted and stored;
+//  * the hand-back arrive carries no memory fence of its own (see mbar_arrive_remote_cta_release).
+//  * EIGHT epilogue warps: a warp may only touch the TMEM lane quarter (warp % 4), so two warps share a quarter and take
+//    half of the tile's columns each — twice the issue slots for the convert / store stream of short-K tiles.
+// The 256 epilogue threads (warps 2..9) of a CTA call these together; named barrier 1 is theirs.
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+template <int BN>
+__device__ __forceinline__ void epi_stage_bias(const Params& p, int n0, float* s_bias, int tid128) {
+  epi_bar();                                   // every warp is done reading the previous tile's slice
+  if (p.bias) {
+    for (int i = tid128; i < BN; i += kEpiThreads) s_bias[i] = (n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.f;
+  }
+  epi_bar();
+}
+
+__device__ __forceinline__ void epi_chunk(const Params& p, long long row, int nb, int split, const uint32_t (&v)[32],
+                                          const float* s_bias_c) {
+  if (row < 0 || nb >= p.N) return;
+  const int ncols = min(32, p.N - nb);
+  if (p.splits > 1) {
+    float* dst = p.partial + ((size_t)split * p.M + row) * p.N + nb;
+    if (ncols == 32 && ((((uintptr_t)dst) & 15) == 0)) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) ((uint4*)dst)[j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) if (j < ncols) dst[j] = __uint_as_float(v[j]);
+    }
+    return;
+  }
+  float x[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    float tt = __uint_as_float(v[j]);
+    if (p.bias) tt += s_bias_c[j];
+    if (p.relu) tt = fmaxf(tt, 0.f);
+    x[j] = tt;
+  }
+  if (p.C) {
+    float* dst = p.C + row * p.ldc + nb;
+    if (ncols == 32 && ((((uintptr_t)dst) & 15) == 0)) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) ((float4*)dst)[j] = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) if (j < ncols) dst[j] = x[j];
+    }
+  }
+  if (p.Chi) {
+    uint32_t hi[16], lo[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float a0 = x[2 * j], a1 = x[2 * j + 1];
+      const __nv_bfloat16 h0 = __float2bfloat16_rn(a0), h1 = __float2bfloat16_rn(a1);
+      hi[j] = pack_bf16x2(a0, a1);
+      lo[j] = pack_bf16x2(a0 - __bfloat162float(h0), a1 - __bfloat162float(h1));
+    }
+    __nv_bfloat16* dh = p.Chi + row * p.ldsplit + nb;
+    __nv_bfloat16* dl = p.Clo + row * p.ldsplit + nb;
+    if (ncols == 32 && ((((uintptr_t)dh) & 15) == 0)) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        ((uint4*)dh)[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+        ((uint4*)dl)[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) if (j < ncols) {
+        __nv_bfloat16 h, l; tc::split_bf16(x[j], h, l);
+        dh[j] = h; dl[j] = l;
+      }
+    }
+  }
+}
+
+// drain one accumulator (this warp's 32 TMEM lanes x BN columns): software-pipelined TMEM reads, two register buffers
+template <int BN>
+__device__ __forceinline__ void epi_tile(const Params& p, long long row, int n0, int split, uint32_t taddr, const float* s_bias) {
+  uint32_t va[32], vb[32];
+  __syncwarp();
+  tc::tmem_ld_32x32(taddr, va);
+#pragma unroll
+  for (int c = 0; c < BN / 32; c += 2) {
+    tc::tmem_ld_wait();
+    if (c + 1 < BN / 32) { __syncwarp(); tc::tmem_ld_32x32(taddr + (uint32_t)((c + 1) * 32), vb); }
+    epi_chunk(p, row, n0 + c * 32, split, va, s_bias + c * 32);
+    if (c + 1 < BN / 32) {
+      tc::tmem_ld_wait();
+      if (c + 2 < BN / 32) { __syncwarp(); tc::tmem_ld_32x32(taddr + (uint32_t)((c + 2) * 32), va); }
+      epi_chunk(p, row, n0 + (c + 1) * 32, split, vb, s_bias + (c + 1) * 32);
+    }
+  }
+}
+
 // Persistent: grid = min(#tiles, #SMs); every role loops over the same static tile sequence.
 template <int BN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
@@ -96,6 +198,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_const
   constexpr int STAGES = Cfg<BN>::STAGES, TILE_B = Cfg<BN>::TILE_B, STAGE_BYTES = Cfg<BN>::STAGE_BYTES;
   constexpr int TMEM_COLS = Cfg<BN>::TMEM_COLS;
   extern __shared__ uint8_t smem_raw[];
+  __shared__ float s_bias[BN];                   // bias slice of the tile being drained (epi_stage_bias)
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = (uint64_t*)(smem + (size_t)STAGES * STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
@@ -109,7 +212,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_const
   if (warp == 0 && lane == 0) {
     tc::prefetch_tmap(&tmAhi); tc::prefetch_tmap(&tmAlo); tc::prefetch_tmap(&tmBhi); tc::prefetch_tmap(&tmBlo);
     for (int s = 0; s < STAGES; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
-    for (int s = 0; s < ACC_STAGES; ++s) { tc::mbar_init(&tfull_bar[s], 1); tc::mbar_init(&tempty_bar[s], 4); }
+    for (int s = 0; s < ACC_STAGES; ++s) { tc::mbar_init(&tfull_bar[s], 1); tc::mbar_init(&tempty_bar[s], 8); }
     tc::fence_barrier_init();
   }
   if (warp == 1) tc::tmem_alloc(tmem_slot, TMEM_COLS);
@@ -183,11 +286,13 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_const
     // ------------------------------------------------------------------ epilogue (warps 2..5)
     const int q = warp & 3;                    // TMEM lane quarter this warp may access
     const int r = q * 32 + lane;               // tile row == TMEM lane
+    const int half = (warp - 2) >> 2;          // which half of the tile's columns (two warps per quarter)
     int it = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
       const TileCoord tl = decode_tile<BN>(p, t);
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
+      epi_stage_bias<BN>(p, tl.n0, s_bias, (int)threadIdx.x - 64);      // while the MMAs of this tile still run
       tc::mbar_wait(&tfull_bar[acc], acc_phase);
       tc::tc_fence_after();
       long long row;                             // output row index (M axis), or -1 when masked
@@ -198,70 +303,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_const
         row = (h < p.H && w < p.W) ? ((long long)tl.img * p.H + h) * p.W + w : -1;
       }
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        __syncwarp();                            // tcgen05.ld is warp-collective: reconverge first
-        uint32_t v[32];
-        tc::tmem_ld_32x32(taddr + (uint32_t)(c * 32), v);
-        tc::tmem_ld_wait();
-        const int nb = tl.n0 + c * 32;
-        if (row < 0 || nb >= p.N) continue;
-        const int ncols = min(32, p.N - nb);
-        if (p.splits > 1) {
-          float* dst = p.partial + ((size_t)tl.split * p.M + row) * p.N + nb;
-          if (ncols == 32 && ((((uintptr_t)dst) & 15) == 0)) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) ((uint4*)dst)[j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) if (j < ncols) dst[j] = __uint_as_float(v[j]);
-          }
-          continue;
-        }
-        float x[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float tt = __uint_as_float(v[j]);
-          if (p.bias && j < ncols) tt += __ldg(p.bias + nb + j);
-          if (p.relu) tt = fmaxf(tt, 0.f);
-          x[j] = tt;
-        }
-        if (p.C) {
-          float* dst = p.C + row * p.ldc + nb;
-          if (ncols == 32 && ((((uintptr_t)dst) & 15) == 0)) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) ((float4*)dst)[j] = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) if (j < ncols) dst[j] = x[j];
-          }
-        }
-        if (p.Chi) {
-          uint32_t hi[16], lo[16];             // packed bf16 pairs, registers only
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float a0 = x[2 * j], a1 = x[2 * j + 1];
-            const __nv_bfloat16 h0 = __float2bfloat16_rn(a0), h1 = __float2bfloat16_rn(a1);
-            hi[j] = pack_bf16x2(a0, a1);
-            lo[j] = pack_bf16x2(a0 - __bfloat162float(h0), a1 - __bfloat162float(h1));
-          }
-          __nv_bfloat16* dh = p.Chi + row * p.ldsplit + nb;
-          __nv_bfloat16* dl = p.Clo + row * p.ldsplit + nb;
-          if (ncols == 32 && ((((uintptr_t)dh) & 15) == 0)) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              ((uint4*)dh)[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-              ((uint4*)dl)[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) if (j < ncols) {
-              __nv_bfloat16 h, l; tc::split_bf16(x[j], h, l);
-              dh[j] = h; dl[j] = l;
-            }
-          }
-        }
-      }
+      epi_tile<BN / 2>(p, row, tl.n0 + half * (BN / 2), tl.split, taddr + (uint32_t)(half * (BN / 2)), s_bias + half * (BN / 2));
       // accumulator drained: hand it back to the MMA warp (4 arrivals, one per epilogue warp)
       tc::tc_fence_before();
       __syncwarp();
@@ -287,7 +329,7 @@ template <int BN_> struct Cfg2 {
   static constexpr int BN = BN_;
   static constexpr int HALF_B = (BN_ / 2) * BK * 2;              // bytes of one B operand half-tile
   static constexpr int STAGE_BYTES = 2 * TILE_A + 2 * HALF_B;    // per CTA
-  static constexpr int STAGES = (BN_ == 256) ? 3 : 4;
+  static constexpr int STAGES = (BN_ == 256) ? 3 : (BN_ == 128 ? 4 : 5);
   static constexpr int TMEM_COLS = ACC_STAGES * BN_;
   static constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
@@ -324,6 +366,7 @@ gemm_bf16x3_2cta_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_
   constexpr int STAGES = Cfg2<BN>::STAGES, HALF_B = Cfg2<BN>::HALF_B, STAGE_BYTES = Cfg2<BN>::STAGE_BYTES;
   constexpr int TMEM_COLS = Cfg2<BN>::TMEM_COLS;
   extern __shared__ uint8_t smem_raw[];
+  __shared__ float s_bias[BN];                   // bias slice of the tile being drained (epi_stage_bias)
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = (uint64_t*)(smem + (size_t)STAGES * STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
@@ -340,7 +383,7 @@ gemm_bf16x3_2cta_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_
   if (warp == 0 && lane == 0) {
     tc::prefetch_tmap(&tmAhi); tc::prefetch_tmap(&tmAlo); tc::prefetch_tmap(&tmBhi); tc::prefetch_tmap(&tmBlo);
     for (int s = 0; s < STAGES; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
-    for (int s = 0; s < ACC_STAGES; ++s) { tc::mbar_init(&tfull_bar[s], 1); tc::mbar_init(&tempty_bar[s], 8); }
+    for (int s = 0; s < ACC_STAGES; ++s) { tc::mbar_init(&tfull_bar[s], 1); tc::mbar_init(&tempty_bar[s], 16); }
     tc::fence_barrier_init();
   }
   if (warp == 1) tc::tmem_alloc_2sm(tmem_slot, TMEM_COLS);
@@ -416,12 +459,14 @@ gemm_bf16x3_2cta_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_
     // ------------------------------------------------------------------ epilogue (warps 2..5 of both CTAs)
     const int q = warp & 3;
     const int r = q * 32 + lane;
+    const int half = (warp - 2) >> 2;
     const uint32_t tempty_leader0 = tc::mapa_shared(tc::smem_u32(&tempty_bar[0]), 0);
     int it = 0;
     for (int t = pair; t < total_tiles; t += npairs, ++it) {
       const TileCoord tl = decode_tile2<BN>(p, t, (int)rank, pm_tiles);
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
+      epi_stage_bias<BN>(p, tl.n0, s_bias, (int)threadIdx.x - 64);
       tc::mbar_wait(&tfull_bar[acc], acc_phase);
       tc::tc_fence_after();
       long long row;
@@ -432,76 +477,207 @@ gemm_bf16x3_2cta_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_
         row = (tl.img < num_images && h < p.H && w < p.W) ? ((long long)tl.img * p.H + h) * p.W + w : -1;
       }
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        __syncwarp();
-        uint32_t v[32];
-        tc::tmem_ld_32x32(taddr + (uint32_t)(c * 32), v);
-        tc::tmem_ld_wait();
-        const int nb = tl.n0 + c * 32;
-        if (row < 0 || nb >= p.N) continue;
-        const int ncols = min(32, p.N - nb);
-        if (p.splits > 1) {
-          float* dst = p.partial + ((size_t)tl.split * p.M + row) * p.N + nb;
-          if (ncols == 32 && ((((uintptr_t)dst) & 15) == 0)) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) ((uint4*)dst)[j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) if (j < ncols) dst[j] = __uint_as_float(v[j]);
-          }
-          continue;
-        }
-        float x[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float tt = __uint_as_float(v[j]);
-          if (p.bias && j < ncols) tt += __ldg(p.bias + nb + j);
-          if (p.relu) tt = fmaxf(tt, 0.f);
-          x[j] = tt;
-        }
-        if (p.C) {
-          float* dst = p.C + row * p.ldc + nb;
-          if (ncols == 32 && ((((uintptr_t)dst) & 15) == 0)) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) ((float4*)dst)[j] = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) if (j < ncols) dst[j] = x[j];
-          }
-        }
-        if (p.Chi) {
-          uint32_t hi[16], lo[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float a0 = x[2 * j], a1 = x[2 * j + 1];
-            const __nv_bfloat16 h0 = __float2bfloat16_rn(a0), h1 = __float2bfloat16_rn(a1);
-            hi[j] = pack_bf16x2(a0, a1);
-            lo[j] = pack_bf16x2(a0 - __bfloat162float(h0), a1 - __bfloat162float(h1));
-          }
-          __nv_bfloat16* dh = p.Chi + row * p.ldsplit + nb;
-          __nv_bfloat16* dl = p.Clo + row * p.ldsplit + nb;
-          if (ncols == 32 && ((((uintptr_t)dh) & 15) == 0)) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              ((uint4*)dh)[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-              ((uint4*)dl)[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) if (j < ncols) {
-              __nv_bfloat16 h, l; tc::split_bf16(x[j], h, l);
-              dh[j] = h; dl[j] = l;
-            }
-          }
-        }
-      }
+      epi_tile<BN / 2>(p, row, tl.n0 + half * (BN / 2), tl.split, taddr + (uint32_t)(half * (BN / 2)), s_bias + half * (BN / 2));
       tc::tc_fence_before();
       __syncwarp();
-      if (lane == 0) tc::mbar_arrive_cluster(tempty_leader0 + (uint32_t)(acc * sizeof(uint64_t)));
+      if (lane == 0) tc::mbar_arrive_remote(tempty_leader0 + (uint32_t)(acc * sizeof(uint64_t)));
     }
   }
   // neither CTA may leave (or free TMEM) while the other can still signal its barriers / read its shared memory
+  tc::tc_fence_before();
+  tc::cluster_sync_all();
+  if (warp == 1) { tc::tc_fence_after(); tc::tmem_dealloc_2sm(tmem_base, TMEM_COLS); }
+}
+
+// ====================================================================================== conv with a shared-memory halo
+// ncu / timing of the tap-by-tap kernels above: conv1_2 (64 -> 64 channels) takes the same 790 us with 64-, 128-wide or
+// 1-CTA tiles — nothing tensor-bound about it. Every 128-pixel A tile is fetched NINE times from L2 (once per tap,
+// shifted), 4.8 GB for that layer = 6.1 TB/s of L2 -> SM traffic, which is the B200's L2 bandwidth; the 256/512-channel
+// layers sit at the same wall (activation tiles 9x + weight tiles once per pixel tile).
+// Here a CTA stages the input HALO of its tile once per 64-channel block — 18 lines x 16 pixels (10 used) x 64 ch, one
+// 4-D TMA box per operand half — and all nine taps are read out of it: the A descriptor of tap (dy, dx) simply starts
+// (dy+1) lines and (dx+1) pixels into the staged block. Tile = 16 lines x 8 pixels, so that one 8-row group of the MMA
+// operand is one line of the tile and consecutive groups are one staged line (16 px x 128 B = 2048 B, a multiple of the
+// 1024-byte swizzle atom) apart: SBO = 2048. L2 traffic for A drops from 9x to 2.25x of the input.
+// Weights still stream per tap through their own ring. CTA pairs (cta_group::2) as above.
+constexpr int HTH = 16, HTW = 8;                       // output tile of one CTA: 16 lines x 8 pixels = 128 rows
+constexpr int HALO_LINES = HTH + 2, HALO_PX = 16;      // staged block: 18 lines x 16 pixels (pixels w0-1 .. w0+14)
+constexpr int HALO_BYTES = HALO_LINES * HALO_PX * 128; // 36 864 B per operand half
+constexpr int HALO_STAGES = 2;
+
+template <int BN_> struct CfgH {
+  static constexpr int HALF_B = (BN_ / 2) * BK * 2;
+  static constexpr int B_STAGE = 2 * HALF_B;
+  static constexpr int B_STAGES = (BN_ == 256) ? 2 : (BN_ == 128 ? 4 : 6);
+  static constexpr int A_STAGE = 2 * HALO_BYTES;
+  static constexpr int TMEM_COLS = ACC_STAGES * BN_;
+  static constexpr size_t SMEM_BYTES = (size_t)HALO_STAGES * A_STAGE + (size_t)B_STAGES * B_STAGE + 1024 + 256;
+};
+
+// 0: tap-by-tap kernels; 1 (default): halo kernel where it measured faster (large maps, few input channels: conv1_2 792 ->
+// 692 us, conv2_2 401 -> 390 us; it loses 5-10 % on the 74x74 / 37x37 maps); 2: halo kernel for every conv (tests).
+int g_halo_mode = 1;
+
+// The start address is a whole number of 128-byte rows into a 1024-byte swizzle atom. Measured on the B200: the 128-byte
+// swizzle is a function of the ABSOLUTE shared-memory address (TMA writes and tcgen05 reads agree without further ado) —
+// with the descriptor's base-offset field set to (addr >> 7) & 7 the results are wrong, with 0 they are exact.
+__device__ __forceinline__ uint64_t umma_desc_halo(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)((HALO_PX * 128) >> 4) << 32;         // SBO: the next 8-row group is the next staged line
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+conv3x3_halo_2cta_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant__ CUtensorMap tmAlo,
+                         const __grid_constant__ CUtensorMap tmBhi, const __grid_constant__ CUtensorMap tmBlo,
+                         const Params p, const int num_images) {
+  constexpr int HALF_B = CfgH<BN>::HALF_B, B_STAGE = CfgH<BN>::B_STAGE, B_STAGES = CfgH<BN>::B_STAGES;
+  constexpr int A_STAGE = CfgH<BN>::A_STAGE, TMEM_COLS = CfgH<BN>::TMEM_COLS;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ float s_bias[BN];                   // bias slice of the tile being drained (epi_stage_bias)
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_b = smem + (size_t)HALO_STAGES * A_STAGE;
+  uint64_t* afull = (uint64_t*)(smem_b + (size_t)B_STAGES * B_STAGE);
+  uint64_t* aempty = afull + HALO_STAGES;
+  uint64_t* bfull = aempty + HALO_STAGES;
+  uint64_t* bempty = bfull + B_STAGES;
+  uint64_t* tfull_bar = bempty + B_STAGES;
+  uint64_t* tempty_bar = tfull_bar + ACC_STAGES;
+  uint32_t* tmem_slot = (uint32_t*)(tempty_bar + ACC_STAGES);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = tc::cluster_ctarank();
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int pm_tiles = (p.m_tiles + 1) >> 1;
+  const int total_tiles = pm_tiles * p.n_tiles;
+  const int cblocks = p.Cin / BK;
+  const int per_img = p.tiles_w * p.tiles_h;
+
+  // this CTA's half of pair-tile t: spatial tile mi = 2*pmi + rank (== m_tiles for the dummy half of an odd last pair)
+  auto decode = [&](int t, int& n0, int& img, int& h0, int& w0) {
+    const int pmi = t / p.n_tiles, ni = t - pmi * p.n_tiles;      // n fastest: the pair's staged activations serve all n tiles from L2
+    const int mi = 2 * pmi + (int)rank;
+    n0 = ni * BN;
+    img = mi / per_img;
+    const int q = mi - img * per_img;
+    const int th = q / p.tiles_w;
+    h0 = th * HTH; w0 = (q - th * p.tiles_w) * HTW;
+  };
+
+  if (warp == 0 && lane == 0) {
+    tc::prefetch_tmap(&tmAhi); tc::prefetch_tmap(&tmAlo); tc::prefetch_tmap(&tmBhi); tc::prefetch_tmap(&tmBlo);
+    for (int s = 0; s < HALO_STAGES; ++s) { tc::mbar_init(&afull[s], 1); tc::mbar_init(&aempty[s], 1); }
+    for (int s = 0; s < B_STAGES; ++s) { tc::mbar_init(&bfull[s], 1); tc::mbar_init(&bempty[s], 1); }
+    for (int s = 0; s < ACC_STAGES; ++s) { tc::mbar_init(&tfull_bar[s], 1); tc::mbar_init(&tempty_bar[s], 16); }
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) tc::tmem_alloc_2sm(tmem_slot, TMEM_COLS);
+  tc::tc_fence_before();
+  tc::cluster_sync_all();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------------------------------------------------------- TMA producer (both CTAs)
+      int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
+      for (int t = pair; t < total_tiles; t += npairs) {
+        int n0, img, h0, w0;
+        decode(t, n0, img, h0, w0);
+        const int nrow = n0 + (int)rank * (BN / 2);
+        for (int cb = 0; cb < cblocks; ++cb) {
+          tc::mbar_wait(&aempty[sa], pa ^ 1);
+          uint8_t* st = smem + (size_t)sa * A_STAGE;
+          if (rank == 0) tc::mbar_expect_tx(&afull[sa], 2 * A_STAGE);
+          const uint32_t fa = tc::mapa_shared(tc::smem_u32(&afull[sa]), 0);
+          tc::tma_load_4d_2sm(st, &tmAhi, fa, cb * BK, w0 - 1, h0 - 1, img);               // out of bounds = zero padding
+          tc::tma_load_4d_2sm(st + HALO_BYTES, &tmAlo, fa, cb * BK, w0 - 1, h0 - 1, img);
+          if (++sa == HALO_STAGES) { sa = 0; pa ^= 1; }
+          for (int tap = 0; tap < 9; ++tap) {
+            tc::mbar_wait(&bempty[sb], pb ^ 1);
+            uint8_t* sbp = smem_b + (size_t)sb * B_STAGE;
+            if (rank == 0) tc::mbar_expect_tx(&bfull[sb], 2 * B_STAGE);
+            const uint32_t fb = tc::mapa_shared(tc::smem_u32(&bfull[sb]), 0);
+            const int kg = tap * cblocks + cb;                                               // weight K order: (kh, kw, cin)
+            tc::tma_load_2d_2sm(sbp, &tmBhi, fb, kg * BK, nrow);
+            tc::tma_load_2d_2sm(sbp + HALF_B, &tmBlo, fb, kg * BK, nrow);
+            if (++sb == B_STAGES) { sb = 0; pb ^= 1; }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      // ---------------------------------------------------------------- MMA issuer (leader CTA)
+      constexpr uint32_t idesc = tc::umma_idesc_bf16_f32(2 * BM, BN);
+      int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
+      int it = 0;
+      for (int t = pair; t < total_tiles; t += npairs, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        tc::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc::tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+        for (int cb = 0; cb < cblocks; ++cb) {
+          tc::mbar_wait(&afull[sa], pa);
+          tc::tc_fence_after();
+          const uint32_t a_base = tc::smem_u32(smem + (size_t)sa * A_STAGE);
+          for (int tap = 0; tap < 9; ++tap) {
+            tc::mbar_wait(&bfull[sb], pb);
+            tc::tc_fence_after();
+            const int ky = tap / 3, kx = tap - ky * 3;                                       // = dy + 1, dx + 1
+            const uint32_t a_off = (uint32_t)(ky * HALO_PX * 128 + kx * 128);
+            const uint32_t sbb = tc::smem_u32(smem_b + (size_t)sb * B_STAGE);
+            const uint64_t b_hi = tc::umma_desc_k_sw128(sbb), b_lo = tc::umma_desc_k_sw128(sbb + HALF_B);
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) {
+              const uint64_t a_hi = umma_desc_halo(a_base + a_off + k * 32);
+              const uint64_t a_lo = umma_desc_halo(a_base + HALO_BYTES + a_off + k * 32);
+              const uint64_t adv = (uint64_t)((k * 16 * 2) >> 4);
+              tc::umma_bf16_2sm(tmem_d, a_hi, b_hi + adv, idesc, (cb | tap | k) != 0);
+              tc::umma_bf16_2sm(tmem_d, a_hi, b_lo + adv, idesc, 1);
+              tc::umma_bf16_2sm(tmem_d, a_lo, b_hi + adv, idesc, 1);
+            }
+            tc::umma_commit_2sm(&bempty[sb], 3);
+            if (++sb == B_STAGES) { sb = 0; pb ^= 1; }
+          }
+          tc::umma_commit_2sm(&aempty[sa], 3);
+          if (++sa == HALO_STAGES) { sa = 0; pa ^= 1; }
+        }
+        tc::umma_commit_2sm(&tfull_bar[acc], 3);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 2..5 of both CTAs)
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int half = (warp - 2) >> 2;
+    const uint32_t tempty_leader0 = tc::mapa_shared(tc::smem_u32(&tempty_bar[0]), 0);
+    int it = 0;
+    for (int t = pair; t < total_tiles; t += npairs, ++it) {
+      int n0, img, h0, w0;
+      decode(t, n0, img, h0, w0);
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      epi_stage_bias<BN>(p, n0, s_bias, (int)threadIdx.x - 64);
+      tc::mbar_wait(&tfull_bar[acc], acc_phase);
+      tc::tc_fence_after();
+      const int h = h0 + r / HTW, w = w0 + (r % HTW);
+      const long long row = (img < num_images && h < p.H && w < p.W) ? ((long long)img * p.H + h) * p.W + w : -1;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+      epi_tile<BN / 2>(p, row, n0 + half * (BN / 2), 0, taddr + (uint32_t)(half * (BN / 2)), s_bias + half * (BN / 2));
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive_remote(tempty_leader0 + (uint32_t)(acc * sizeof(uint64_t)));
+    }
+  }
   tc::tc_fence_before();
   tc::cluster_sync_all();
   if (warp == 1) { tc::tc_fence_after(); tc::tmem_dealloc_2sm(tmem_base, TMEM_COLS); }
@@ -565,13 +741,30 @@ bool make_tmap_nhwc(CUtensorMap* m, const void* ptr, int B, int H, int W, int C)
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// 4D NHWC bf16 activation [B,H,W,C] -> halo box {64, 16 px, 18 lines, 1}
+bool make_tmap_halo(CUtensorMap* m, const void* ptr, int B, int H, int W, int C) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)HALO_PX, (cuuint32_t)HALO_LINES, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 int ensure_attr() {
   static bool done = false;
   if (!done) {
     MB200_CHECK(cudaFuncSetAttribute(gemm_bf16x3_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<128>::SMEM_BYTES));
     MB200_CHECK(cudaFuncSetAttribute(gemm_bf16x3_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<256>::SMEM_BYTES));
+    MB200_CHECK(cudaFuncSetAttribute(gemm_bf16x3_2cta_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg2<64>::SMEM_BYTES));
     MB200_CHECK(cudaFuncSetAttribute(gemm_bf16x3_2cta_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg2<128>::SMEM_BYTES));
     MB200_CHECK(cudaFuncSetAttribute(gemm_bf16x3_2cta_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg2<256>::SMEM_BYTES));
+    MB200_CHECK(cudaFuncSetAttribute(conv3x3_halo_2cta_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CfgH<64>::SMEM_BYTES));
+    MB200_CHECK(cudaFuncSetAttribute(conv3x3_halo_2cta_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CfgH<128>::SMEM_BYTES));
+    MB200_CHECK(cudaFuncSetAttribute(conv3x3_halo_2cta_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CfgH<256>::SMEM_BYTES));
     done = true;
   }
   return MB200_OK;
@@ -603,10 +796,10 @@ inline int pick_pair_bn(long long m_tiles, int N, int splits, int bn1) {
   const int pairs = kNumSMs / 2;
   const double rows = (double)m_tiles / (double)(2 * pm);                     // the dummy half of an odd last pair
   double best = 0.0; int best_bn = 0;
-  for (int bn = 128; bn <= 256; bn += 128) {
-    if (bn == 256 && N < 256) continue;
+  for (int bn = 64; bn <= 256; bn *= 2) {       // 64-wide tiles only where a 128-wide one would be half padding (conv1_2: Cout = 64)
+    if ((bn == 256 && N < 256) || (bn == 64 && N > 64)) continue;
     const double colw = (double)N / (double)(((N + bn - 1) / bn) * bn);
-    const double e = wave_eff(pm * ((N + bn - 1) / bn), pairs) * colw * rows * (bn == 256 ? 1.0 : 0.93);
+    const double e = wave_eff(pm * ((N + bn - 1) / bn), pairs) * colw * rows * (bn == 256 ? 1.0 : (bn == 128 ? 0.93 : 0.8));
     if (e > best) { best = e; best_bn = bn; }
   }
   if (g_pair_mode == 2) return best_bn;
@@ -625,8 +818,10 @@ int launch(const CUtensorMap& ahi, const CUtensorMap& alo, const CUtensorMap& bh
     const int grid = 2 * (int)min(tiles, (long long)(kNumSMs / 2));         // persistent: one CTA pair per TPC
     if (pair_bn == 256)
       gemm_bf16x3_2cta_kernel<256><<<grid, kGemmThreads, Cfg2<256>::SMEM_BYTES, stream>>>(ahi, alo, bhi, blo, p, num_images);
-    else
+    else if (pair_bn == 128)
       gemm_bf16x3_2cta_kernel<128><<<grid, kGemmThreads, Cfg2<128>::SMEM_BYTES, stream>>>(ahi, alo, bhi, blo, p, num_images);
+    else
+      gemm_bf16x3_2cta_kernel<64><<<grid, kGemmThreads, Cfg2<64>::SMEM_BYTES, stream>>>(ahi, alo, bhi, blo, p, num_images);
     MB200_CHECK_LAUNCH("gemm_bf16x3_2cta_kernel");
     return MB200_OK;
   }
@@ -711,6 +906,39 @@ int mb200_conv3x3_bf16x3(const void* xhi, const void* xlo, const void* whi, cons
   if (Cin % BK != 0) return MB200_ERR_ARG;
   CUtensorMap ta, tal, tb, tbl;
   const long long Kp = 9LL * Cin;
+  if (g_pair_mode != 0 && (g_halo_mode == 2 || (g_halo_mode == 1 && Cin <= 128 && (long long)H * W >= 80000))) {
+    // halo kernel: 16 x 8 pixel tiles, always CTA pairs (a single tile gets a dummy partner)
+    const int tw = mb200_div_up(W, HTW), th = mb200_div_up(H, HTH);
+    const long long sp = (long long)B * tw * th;
+    int bn = 64;
+    if (Cout > 64) {
+      const long long pm = (sp + 1) / 2;
+      const double e128 = wave_eff(pm * ((Cout + 127) / 128), kNumSMs / 2) * ((double)Cout / (((Cout + 127) / 128) * 128)) * 0.93;
+      const double e256 = wave_eff(pm * ((Cout + 255) / 256), kNumSMs / 2) * ((double)Cout / (((Cout + 255) / 256) * 256));
+      bn = (Cout >= 256 && e256 >= e128) ? 256 : 128;
+    }
+    if (!make_tmap_halo(&ta, xhi, B, H, W, Cin) || !make_tmap_halo(&tal, xlo, B, H, W, Cin) ||
+        !make_tmap_2d(&tb, whi, Cout, Kp, bn / 2) || !make_tmap_2d(&tbl, wlo, Cout, Kp, bn / 2)) {
+      mb200_set_error("cuTensorMapEncodeTiled", cudaErrorInvalidValue);
+      return MB200_ERR_CUDA;
+    }
+    int rc = ensure_attr();
+    if (rc != MB200_OK) return rc;
+    Params p = {};
+    p.M = B * H * W; p.N = Cout; p.splits = 1; p.kblocks = (int)(Kp / BK);
+    p.C = y; p.ldc = Cout; p.Chi = (__nv_bfloat16*)yhi; p.Clo = (__nv_bfloat16*)ylo; p.ldsplit = Cout;
+    p.bias = bias; p.relu = relu; p.partial = nullptr;
+    p.conv = 1; p.H = H; p.W = W; p.Cin = Cin; p.tiles_w = tw; p.tiles_h = th;
+    p.m_tiles = (int)sp; p.n_tiles = mb200_div_up(Cout, bn);
+    const long long tiles = ((sp + 1) / 2) * p.n_tiles;
+    if (tiles > 0x7fffffffLL) return MB200_ERR_UNSUPPORTED;
+    const int grid = 2 * (int)min(tiles, (long long)(kNumSMs / 2));
+    if (bn == 256) conv3x3_halo_2cta_kernel<256><<<grid, kGemmThreads, CfgH<256>::SMEM_BYTES, stream>>>(ta, tal, tb, tbl, p, B);
+    else if (bn == 128) conv3x3_halo_2cta_kernel<128><<<grid, kGemmThreads, CfgH<128>::SMEM_BYTES, stream>>>(ta, tal, tb, tbl, p, B);
+    else conv3x3_halo_2cta_kernel<64><<<grid, kGemmThreads, CfgH<64>::SMEM_BYTES, stream>>>(ta, tal, tb, tbl, p, B);
+    MB200_CHECK_LAUNCH("conv3x3_halo_2cta_kernel");
+    return MB200_OK;
+  }
   const long long sp_tiles = (long long)B * mb200_div_up(W, TW) * mb200_div_up(H, TH);
   const int bn = pick_bn(sp_tiles, Cout);
   const int pair_bn = pick_pair_bn(sp_tiles, Cout, 1, bn);
@@ -727,6 +955,14 @@ int mb200_conv3x3_bf16x3(const void* xhi, const void* xlo, const void* whi, cons
   p.conv = 1; p.H = H; p.W = W; p.Cin = Cin; p.tiles_w = mb200_div_up(W, TW); p.tiles_h = mb200_div_up(H, TH);
   p.m_tiles = B * p.tiles_w * p.tiles_h; p.n_tiles = mb200_div_up(Cout, pair_bn ? pair_bn : bn);
   return launch(ta, tal, tb, tbl, p, bn, pair_bn, B, stream);
+}
+
+/* conv3x3 kernel selection: 0 = tap-by-tap implicit GEMM (shifted TMA boxes), 1 = per layer (default: the shared-memory
+ * halo kernel for large maps with <= 128 input channels), 2 = halo kernel always. Returns the previous mode. */
+int mb200_conv_set_halo_mode(int mode) {
+  const int old = g_halo_mode;
+  if (mode >= 0 && mode <= 2) g_halo_mode = mode;
+  return old;
 }
 
 /* 0: 1-CTA kernels only; 1: per-shape choice (default); 2: the CTA-pair (cta_group::2) kernel whenever the shape allows.

@@ -164,9 +164,19 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar, uint16_t cta_mask
 }
 
 // fp32 -> (hi, lo) bf16 pair with hi + lo == x to ~2^-17 relative.
+// (An integer-rounding variant — (u + 0x7FFF + lsb) >> 16, bit-identical to cvt.rn for non-NaN inputs — was measured in
+// round 2 because ncu showed the XU (conversion) pipe 60 % busy in the short-K conv kernels: it was SLOWER everywhere
+// (conv1_2 792 -> 880 us): the epilogue is latency-bound, not XU-bound, and the extra ALU instructions lengthen it.)
 __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
   hi = __float2bfloat16_rn(x);
   lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+
+// cluster-remote mbarrier arrive without a fence of its own (cutlass::arch::ClusterBarrier::arrive(cta_id) uses the same
+// form). The accumulator hand-back needs tcgen05 ordering only (tcgen05.fence::before_thread_sync precedes it);
+// `.release.cluster` put a MEMBAR.ALL.GPU + ERRBAR in front of every arrive (ncu: 9 % of the conv1_2 kernel's samples).
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 
 }  // namespace tc

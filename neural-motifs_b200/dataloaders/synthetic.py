@@ -58,6 +58,9 @@ class SyntheticBlob(object):
 
     def scatter(self):
         self.dev = {k: v.to(self.device, non_blocking=True) for k, v in self.host.items()}
+        # the labels exist on the host already: RelModel.forward takes the image index / foreground test from here instead
+        # of reading gt_classes back from the device (lib/rel_model.py EARLY_HOST_INDS)
+        self.dev["gt_classes"]._mb200_host = self.host["gt_classes"].numpy()
 
     def __getitem__(self, index):
         if index != 0:

@@ -73,3 +73,21 @@ class GradAllReducer(object):
     def all_reduce(self):
         self.start()
         self.wait()
+
+
+def count_weighted_loss(sums_and_counts):
+    """Data-parallel loss whose gradient, once all-reduced and divided by the world size (lib/fused_optim.FlatSGD folds
+    the 1/world into its update), equals the gradient of the reference's loss: there all GPUs' outputs are gathered on
+    GPU 0 and ONE mean is taken over the concatenated objects / relations (models/train_rels.py:140-141 after
+    `gather_res`, lib/object_detector.py:40-47), i.e. every element weighs 1/N_total — a per-rank mean would weigh the
+    elements of a rank that holds fewer of them more. `sums_and_counts`: [(sum-reduced loss tensor, local element
+    count), ...]; returns  sum_k  loss_sum_k * world / N_total_k  (one tiny all-reduce of the counts; with one rank, or
+    equal counts everywhere, this is exactly the plain per-rank mean)."""
+    world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+    if world == 1:
+        return sum(s / max(int(n), 1) for s, n in sums_and_counts)
+    dev = sums_and_counts[0][0].device
+    tot = torch.tensor([float(n) for _, n in sums_and_counts], device=dev, dtype=torch.float32)
+    dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    tot = tot.clamp_min(1.0)
+    return sum(s * (world / tot[k]) for k, (s, _) in enumerate(sums_and_counts))

@@ -104,7 +104,32 @@ class DecoderRNN(torch.nn.Module):
         dists = tc_ops.linear_tc(h_packed, self.out.weight, self.out.bias)
         return dists, labels.clone()
 
-    def forward(self, inputs, initial_state=None, labels=None, boxes_for_nms=None, dropout_mask=None):
+    def _commit_with_overlaps(self, boxes, probs):
+        import motifs_cabi as _c
+        N, C = probs.shape
+        dev = probs.device
+        if N * C * 4 <= 200 * 1024:
+            boxes = boxes.contiguous().float(); probs = probs.contiguous().float()
+            commit = torch.empty(N, dtype=torch.long, device=dev)
+            with torch.cuda.device(dev):
+                rc = _c.load().mb200_decoder_commit(_c.ptr(boxes), _c.ptr(probs), N, C, float(self.nms_thresh), _c.ptr(commit),
+                                                    _c.cur_stream())
+            _c.check(rc, "mb200_decoder_commit")
+            return commit
+        is_overlap = nms_overlaps(boxes).view(N, N, C).cpu().numpy() >= self.nms_thresh
+        sampled = probs.cpu().numpy()
+        sampled[:, 0] = 0
+        commit = np.zeros(N, dtype=np.int64)
+        for i in range(N):
+            box_ind, cls_ind = np.unravel_index(sampled.argmax(), sampled.shape)
+            commit[int(box_ind)] = int(cls_ind)
+            sampled[is_overlap[box_ind, :, cls_ind], cls_ind] = 0.0
+            sampled[box_ind] = -1.0
+        return torch.as_tensor(commit, device=dev)
+
+    def forward(self, inputs, initial_state=None, labels=None, boxes_for_nms=None, dropout_mask=None, labels_all_fg=None):
+        """`labels_all_fg` (superset of the reference signature): whether every label is foreground, when the caller
+        already holds the labels on the host; None = read it back here (one D2H)."""
         if not isinstance(inputs, PackedSequence):
             raise ValueError('inputs must be PackedSequence but got %s' % (type(inputs)))
         sequence_tensor, batch_lengths = inputs[0], inputs[1]
@@ -116,7 +141,8 @@ class DecoderRNN(torch.nn.Module):
             dropout_mask = get_dropout_mask(self.recurrent_dropout_probability,
                                             torch.empty(batch_size, H, device=dev))
 
-        if self.training and initial_state is None and labels is not None and bool((labels > 0).all()):
+        if self.training and initial_state is None and labels is not None and \
+                (labels_all_fg if labels_all_fg is not None else bool((labels > 0).all())):
             return self._forward_teacher_forced(sequence_tensor, batch_lengths, labels, dropout_mask)
 
         # ---------------------------------------------------------------- step loop (decoder_rnn.py:160-227)
@@ -156,18 +182,9 @@ class DecoderRNN(torch.nn.Module):
                 previous_embed = self.obj_embed(best_ind + 1)
 
         if boxes_for_nms is not None and not self.training:
-            # overlap-aware greedy commitment (decoder_rnn.py:230-247); host loop as in the reference
-            is_overlap = nms_overlaps(boxes_for_nms.detach()).view(
-                boxes_for_nms.size(0), boxes_for_nms.size(0), boxes_for_nms.size(1)).cpu().numpy() >= self.nms_thresh
-            out_dists_sampled = F.softmax(torch.cat(out_dists, 0), 1).detach().cpu().numpy()
-            out_dists_sampled[:, 0] = 0
-            commit = np.zeros(len(out_commitments), dtype=np.int64)
-            for i in range(commit.shape[0]):
-                box_ind, cls_ind = np.unravel_index(out_dists_sampled.argmax(), out_dists_sampled.shape)
-                commit[int(box_ind)] = int(cls_ind)
-                out_dists_sampled[is_overlap[box_ind, :, cls_ind], cls_ind] = 0.0
-                out_dists_sampled[box_ind] = -1.0
-            out_commitments = torch.as_tensor(commit, device=dev)
+            # overlap-aware greedy commitment (decoder_rnn.py:230-247): one single-CTA kernel (csrc/boxes.cu) instead of the
+            # reference's D2H of the [N,N,C] overlaps + host loop; the host loop remains for > ~330 detections
+            out_commitments = self._commit_with_overlaps(boxes_for_nms.detach(), F.softmax(torch.cat(out_dists, 0), 1).detach())
         else:
             out_commitments = torch.cat(out_commitments, 0)
         return torch.cat(out_dists, 0), out_commitments

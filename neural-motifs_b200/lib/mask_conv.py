@@ -15,7 +15,8 @@ import torch
 from torch.autograd import Function
 
 import motifs_cabi as _c
-from lib.tc_ops import SplitMat, gemm, split_rows, split_transposed, _cached, _round_up
+from lib import tc_ops
+from lib.tc_ops import SplitMat, gemm, gemm_mn, split_rows, split_transposed, _cached, _round_up
 
 
 def _lib_call(name, dev, *args):
@@ -127,7 +128,8 @@ class _MaskConvNet(Function):
         H1 = (S - 1) // 2 + 1
         H2 = (H1 - 1) // 2 + 1
         # conv1 (+bias, ReLU) -> y1 NHWC [R*H1*H1, C1]
-        y1 = gemm(_im2col7s2(masks, False), _w_stem(w1), bias=b1.detach(), relu=True)
+        col1 = _im2col7s2(masks, False)
+        y1 = gemm(col1, _w_stem(w1), bias=b1.detach(), relu=True)
         if training:
             mean1, inv1 = _bn_stats(y1, bn1.eps, bn1.momentum, bn1.running_mean, bn1.running_var)
         else:
@@ -137,7 +139,8 @@ class _MaskConvNet(Function):
         _lib_call("mb200_bn_pool3s2_nhwc", dev, _c.ptr(y1), _c.ptr(mean1), _c.ptr(inv1), _c.ptr(g1.detach()),
                   _c.ptr(be1.detach()), R, H1, H1, C1, _c.ptr(p1), _c.ptr(arg1))
         # conv2 (+bias, ReLU) -> y2 NHWC [R*H2*H2, C2]
-        y2 = gemm(_im2col3(p1, False), _w3(w2), bias=b2.detach(), relu=True)
+        col2 = _im2col3(p1, False)
+        y2 = gemm(col2, _w3(w2), bias=b2.detach(), relu=True)
         if training:
             mean2, inv2 = _bn_stats(y2, bn2.eps, bn2.momentum, bn2.running_mean, bn2.running_var)
         else:
@@ -150,6 +153,9 @@ class _MaskConvNet(Function):
         ctx.dims = (R, S, H1, H2, C1, C2)
         ctx.has_addend = addend is not None
         ctx.save_for_backward(masks, y1, mean1, inv1, arg1, p1, y2, mean2, inv2, w1, g1, w2, g2)
+        # the plain im2col pairs are the B operands of the weight-gradient GEMMs on the MN-major kernel (dW = dz^T col):
+        # keeping them (0.85 GB at 1536 relations) removes the transposed im2col passes of backward
+        ctx.cols = (col1, col2) if (training and tc_ops.GEMM_MN and not FUSED_BWD) else None
         return out
 
     @staticmethod
@@ -167,11 +173,15 @@ class _MaskConvNet(Function):
             dz2_t, dz2_p, dg2, dbe2, db2 = _bn_relu_backward_split(g_nhwc, None, y2, mean2, inv2, g2.detach(), H2, H2, True)
         else:
             dz2, dg2, dbe2, db2 = _bn_relu_backward(g_nhwc, y2, mean2, inv2, g2.detach())
-            dz2_t, dz2_p = split_transposed(dz2), split_rows(dz2)
+            dz2_p = split_rows(dz2)
+            dz2_t = split_transposed(dz2) if ctx.cols is None else None
             del dz2
         del g_nhwc
         # conv2: dW2 = dz2^T @ im2col(p1);  dp1 = col2im(dz2 @ W2mat)
-        dw2 = gemm(dz2_t, _im2col3(p1, True))                                         # [C2, 9*C1]
+        if ctx.cols is not None:
+            dw2 = gemm_mn(dz2_p, ctx.cols[1])                                         # [C2, 9*C1], no transposed operands
+        else:
+            dw2 = gemm(dz2_t, _im2col3(p1, True))                                     # [C2, 9*C1]
         dw2 = dw2.view(C2, 3, 3, C1).permute(0, 3, 1, 2).contiguous()
         dcol = gemm(dz2_p, _w3_t(w2))                                                 # [P2, 9*C1]
         del dz2_t, dz2_p
@@ -186,10 +196,14 @@ class _MaskConvNet(Function):
             _lib_call("mb200_unpool3s2_nhwc", dev, _c.ptr(dp1), _c.ptr(arg1), R, H1, H1, C1, _c.ptr(dbn1))
             dz1, dg1, dbe1, db1 = _bn_relu_backward(dbn1, y1, mean1, inv1, g1.detach())
             del dbn1
-            dz1_t = split_transposed(dz1)
+            dz1_t = split_transposed(dz1) if ctx.cols is None else split_rows(dz1)
             del dz1
         # conv1: dW1 = dz1^T @ im2col(masks) (the masks themselves need no gradient)
-        dw1 = gemm(dz1_t, _im2col7s2(masks, True))                                    # [C1, 128]
+        if ctx.cols is not None:
+            dw1 = gemm_mn(dz1_t, ctx.cols[0])                                         # [C1, 128]
+            ctx.cols = None
+        else:
+            dw1 = gemm(dz1_t, _im2col7s2(masks, True))                                # [C1, 128]
         dw1 = dw1[:, :98].reshape(C1, 7, 7, 2).permute(0, 3, 1, 2).contiguous()
         return (None, g if ctx.has_addend else None, dw1, db1, dg1, dbe1, dw2, db2, dg2, dbe2, None, None, None)
 

@@ -260,6 +260,9 @@ class ObjectDetector(nn.Module):
         already read back; with it the GT-box assignment — whose `nonzero` needs the host anyway — runs BEFORE the
         backbone is queued, so the host never waits on the backbone."""
         frozen = not any(p.requires_grad for p in self.parameters())
+        if not frozen:          # a deferred optimizer update of these parameters may be in flight (lib/fused_optim.py)
+            from lib import fused_optim
+            fused_optim.wait_pending_updates()
         with torch.set_grad_enabled(torch.is_grad_enabled() and not frozen):
             return self._forward(x, im_sizes, image_offset, gt_boxes, gt_classes, gt_rels, proposals,
                                  train_anchor_inds, return_fmap, im_inds_host)

@@ -20,7 +20,7 @@ from torch.nn import functional as F
 from torch.nn.utils.rnn import PackedSequence
 
 from config import BATCHNORM_MOMENTUM
-from lib import tc_ops
+from lib import fused_optim, tc_ops
 from lib.fpn.box_utils import bbox_overlaps, center_size
 from lib.fpn.nms.functions.nms import apply_nms
 from lib.fpn.roi_align.functions.roi_align import RoIAlignFunction, roi_align_from_nhwc
@@ -37,8 +37,11 @@ MODES = ('sgdet', 'sgcls', 'predcls')
 
 # With GT boxes (sgcls / predcls) the image index of every object is an INPUT (gt_classes[:, 0]): read it back once,
 # before the backbone is queued, and hand the host copy to the code that builds the packed-sequence order, instead of
-# three D2H reads in the middle of forward (each one drains the stream). "0" keeps the reference's read-back points.
-EARLY_HOST_INDS = os.environ.get("MOTIFS_EARLY_HOST_INDS", "0") == "1"
+# D2H reads in the middle of forward (each one drains the stream, after which the GPU idles while the host queues the small
+# kernels of the context code one by one): the same read-back also tells whether every label is foreground, which is what
+# the decoder's teacher-forcing test (decoder_rnn.py:206-213) would otherwise read back after the object-context LSTM.
+# With the early read the host queues the whole forward while the backbone runs. "0" keeps the reference's read-back points.
+EARLY_HOST_INDS = os.environ.get("MOTIFS_EARLY_HOST_INDS", "1") == "1"
 
 
 def _sort_by_score(im_inds, scores, host=None):
@@ -57,7 +60,9 @@ def _sort_by_score(im_inds, scores, host=None):
     inds = torch.as_tensor(inds, dtype=torch.long, device=im_inds.device)
     rpi = torch.as_tensor(rois_per_image, device=im_inds.device)
     roi_order = scores - 2 * rpi[im_inds]
-    _, perm = torch.sort(roi_order, 0, descending=True)
+    # stable: objects whose keys tie exactly (PredCls ordered by confidence: every confidence is 1.0) keep their input
+    # order, as in the oracle; an unstable sort leaves the order to the backend (CPU and CUDA differ)
+    _, perm = torch.sort(roi_order, dim=0, descending=True, stable=True)
     perm = perm[inds]
     _, inv_perm = torch.sort(perm)
     return perm, inv_perm, ls_transposed
@@ -161,7 +166,7 @@ class LinearizedContext(nn.Module):
         return edge_reps[inv_perm]
 
     def obj_ctx(self, obj_feats, obj_dists, im_inds, obj_labels=None, box_priors=None, boxes_per_cls=None,
-                im_inds_host=None):
+                im_inds_host=None, labels_all_fg=None):
         """rel_model.py:197-234."""
         confidence = F.softmax(obj_dists, dim=1).detach()[:, 1:].max(1)[0]
         perm, inv_perm, ls_transposed = self.sort_rois(im_inds.detach(), confidence, box_priors, im_inds_host)
@@ -174,7 +179,7 @@ class LinearizedContext(nn.Module):
             obj_dists, obj_preds = self.decoder_rnn(
                 decoder_inp, labels=obj_labels[perm] if obj_labels is not None else None,
                 boxes_for_nms=boxes_per_cls[perm] if boxes_per_cls is not None else None,
-                dropout_mask=self._mask("decoder_rnn"))
+                dropout_mask=self._mask("decoder_rnn"), labels_all_fg=labels_all_fg)
             obj_preds = obj_preds[inv_perm]
             obj_dists = obj_dists[inv_perm]
         else:
@@ -185,8 +190,9 @@ class LinearizedContext(nn.Module):
         return obj_dists, obj_preds, encoder_rep
 
     def forward(self, obj_fmaps, obj_logits, im_inds, obj_labels=None, box_priors=None, boxes_per_cls=None,
-                im_inds_host=None):
-        """rel_model.py:236-296. `im_inds_host`: optional numpy copy of im_inds the caller already holds."""
+                im_inds_host=None, labels_all_fg=None):
+        """rel_model.py:236-296. `im_inds_host`: optional numpy copy of im_inds the caller already holds;
+        `labels_all_fg`: whether every entry of `obj_labels` is > 0, when the caller already knows (else read back)."""
         obj_embed = tc_ops.matmul_tc(F.softmax(obj_logits, dim=1), self.obj_embed.weight, self.obj_embed.weight, "E")
         pe = self.pos_embed
         pos = pe[0](center_size(box_priors))
@@ -197,7 +203,7 @@ class LinearizedContext(nn.Module):
 
         if self.nl_obj > 0:
             obj_dists2, obj_preds, obj_ctx = self.obj_ctx(obj_pre_rep, obj_logits, im_inds, obj_labels, box_priors,
-                                                          boxes_per_cls, im_inds_host)
+                                                          boxes_per_cls, im_inds_host, labels_all_fg)
         else:
             if self.mode == 'predcls':
                 obj_dists2 = to_onehot(obj_labels.detach(), self.num_classes)
@@ -296,10 +302,19 @@ class RelModel(nn.Module):
                 x = m(x)
         return x
 
+    def _nhwc_of(self, features):
+        """The detector's NHWC copy of `features` iff `features` IS the map it produced last (same memory) and carries no
+        gradient; anything else (another map, a micro-batch, a trainable backbone) takes the NCHW autograd path."""
+        nh = self.detector._fmap_nhwc
+        if nh is None or features.requires_grad or features.data_ptr() != nh.data_ptr() or \
+                tuple(features.shape) != (nh.size(0), nh.size(3), nh.size(1), nh.size(2)):
+            return None
+        return nh
+
     def visual_rep(self, features, rois, pair_inds):
         """Union-box visual features -> fc6/fc7 (no final ReLU) (rel_model.py:403-414)."""
         assert pair_inds.size(1) == 2
-        uboxes = self.union_boxes(features, rois, pair_inds, fmap_nhwc=self.detector._fmap_nhwc)
+        uboxes = self.union_boxes(features, rois, pair_inds, fmap_nhwc=self._nhwc_of(features))
         return self._run_roi_fmap(uboxes)
 
     def get_rel_inds(self, rel_labels, im_inds, box_priors):
@@ -317,8 +332,8 @@ class RelModel(nn.Module):
 
     def obj_feature_map(self, features, rois):
         """RoIAlign + the trainable fc6/fc7 copy (rel_model.py:439-448)."""
-        nh = self.detector._fmap_nhwc
-        if nh is not None and not features.requires_grad:
+        nh = self._nhwc_of(features)
+        if nh is not None:
             pool = roi_align_from_nhwc(nh, rois, self.pooling_size, self.pooling_size, 1 / 16)
         else:
             pool = RoIAlignFunction(self.pooling_size, self.pooling_size, spatial_scale=1 / 16)(features, rois)
@@ -326,11 +341,22 @@ class RelModel(nn.Module):
 
     def forward(self, x, im_sizes, image_offset, gt_boxes=None, gt_classes=None, gt_rels=None, proposals=None,
                 train_anchor_inds=None, return_fmap=False):
-        im_inds_host = None
+        im_inds_host = labels_all_fg = None
         if EARLY_HOST_INDS and self.detector.mode == 'gtbox' and gt_classes is not None:
-            im_inds_host = (gt_classes[:, 0] - image_offset).cpu().numpy()      # the one early read-back
+            gtc = getattr(gt_classes, "_mb200_host", None)                      # the loader's host copy (dataloaders/synthetic.py) ...
+            if gtc is None or gtc.shape != tuple(gt_classes.shape):
+                gtc = gt_classes.cpu().numpy()                                  # ... else the one early read-back
+            im_inds_host = gtc[:, 0] - image_offset
+            labels_all_fg = bool((gtc[:, 1] > 0).all())                         # rm_obj_labels = gt_classes[:, 1] in gtbox mode
+        # A deferred optimizer update (lib/fused_optim.FlatSGD(defer_step=True): gradient all-reduce + fused SGD on a side
+        # stream) may still be in flight. A frozen detector (models/train_rels.py:51-52) reads none of the parameters being
+        # updated, so it runs underneath; everything after it waits here.
+        det_frozen = not any(p.requires_grad for p in self.detector.parameters())
+        if not det_frozen:
+            fused_optim.wait_pending_updates()
         result = self.detector(x, im_sizes, image_offset, gt_boxes, gt_classes, gt_rels, proposals,
                                train_anchor_inds, return_fmap=True, im_inds_host=im_inds_host)
+        fused_optim.wait_pending_updates()
         if result.is_none():
             return ValueError("heck")   # rel_model.py:474-475 returns (does not raise) this
 
@@ -350,7 +376,7 @@ class RelModel(nn.Module):
         result.rm_obj_dists, result.obj_preds, edge_ctx = self.context(
             result.obj_fmap, result.rm_obj_dists.detach(), im_inds,
             result.rm_obj_labels if self.training or self.mode == 'predcls' else None,
-            boxes.detach(), result.boxes_all, im_inds_host=im_inds_host)
+            boxes.detach(), result.boxes_all, im_inds_host=im_inds_host, labels_all_fg=labels_all_fg)
 
         if edge_ctx is None:
             edge_rep = self.post_emb(result.obj_preds)
@@ -375,6 +401,7 @@ class RelModel(nn.Module):
                 result.obj_preds[rel_inds[:, 1]], result.obj_preds[rel_inds[:, 2]]), 1))
         if getattr(self, "keep_last_result", False):
             self.last_result = result          # debugging / parity tests: logits before filter_dets
+        self.detector._fmap_nhwc = self.detector._fmap_split = None     # do not pin this batch's feature map until the next one
         if self.training:
             return result
 

@@ -66,6 +66,8 @@ SIGNATURES = {
     "mb200_sgd_momentum_clip_scaled": (c_int, [P, P, P, c_longlong, c_float, c_float, c_float, P, c_float, c_float, c_int, c_int, P]),
     "mb200_anchor_targets": (c_int, [P, c_int, P, c_int, c_double, c_double, P, P, P, P, P]),
     "mb200_gemm_set_pair_mode": (c_int, [c_int]),
+    "mb200_conv_set_halo_mode": (c_int, [c_int]),
+    "mb200_decoder_commit": (c_int, [P, P, c_int, c_int, c_float, P, P]),
     "mb200_sgemm": (c_int, [c_int, c_int, c_int, c_int, c_int, c_float, P, c_int, P, c_int, c_float, P, c_int, P]),
 }
 
@@ -94,6 +96,12 @@ def load():
         fn.restype = res
         fn.argtypes = args
     _lib = lib
+    mode = os.environ.get("MOTIFS_GEMM_PAIR_MODE")      # A/B runs: 0 = 1-CTA tcgen05 kernels only, 1 = per shape (default), 2 = force pairs
+    if mode is not None:
+        lib.mb200_gemm_set_pair_mode(int(mode))
+    mode = os.environ.get("MOTIFS_CONV_HALO_MODE")      # 0 = tap-by-tap conv kernels, 1 = halo kernel (default)
+    if mode is not None:
+        lib.mb200_conv_set_halo_mode(int(mode))
     return lib
 
 

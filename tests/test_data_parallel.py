@@ -240,6 +240,46 @@ def test_flat_sgd_ranks_with_different_graphs_gloo_world2():
     assert out["raised0"] is True and out["raised1"] is True
 
 
+def _worker_weighted(rank, world, port, out):
+    """Ranks holding different numbers of objects / relations: the count-weighted loss + SUM all-reduce + 1/world must
+    reproduce the gradient of ONE mean over the concatenated elements (the reference gathers to GPU 0 and averages)."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "neural-motifs_b200"))
+    from lib.data_parallel import init_from_env, count_weighted_loss
+    import torch.nn.functional as F
+    init_from_env("gloo")
+    torch.manual_seed(0)
+    w = torch.nn.Parameter(torch.randn(5, 7))
+    n_obj, n_rel = (3, 11) if rank == 0 else (9, 2)
+    g = torch.Generator().manual_seed(10 + rank)
+    xo, yo = torch.randn(n_obj, 7, generator=g), torch.randint(0, 5, (n_obj,), generator=g)
+    xr, yr = torch.randn(n_rel, 7, generator=g), torch.randint(0, 5, (n_rel,), generator=g)
+    loss = count_weighted_loss([(F.cross_entropy(xo @ w.t(), yo, reduction='sum'), n_obj),
+                                (F.cross_entropy(xr @ w.t(), yr, reduction='sum'), n_rel)])
+    loss.backward()
+    grad = w.grad.clone()
+    dist.all_reduce(grad)
+    out[rank] = grad / world
+    out[10 + rank] = (xo, yo, xr, yr)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_count_weighted_loss_matches_gathered_mean_gloo_world2():
+    import torch.nn.functional as F
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker_weighted, args=(2, _free_port(), out), nprocs=2, join=True)
+    torch.manual_seed(0)
+    w = torch.nn.Parameter(torch.randn(5, 7))
+    xo = torch.cat((out[10][0], out[11][0])); yo = torch.cat((out[10][1], out[11][1]))
+    xr = torch.cat((out[10][2], out[11][2])); yr = torch.cat((out[10][3], out[11][3]))
+    (F.cross_entropy(xo @ w.t(), yo) + F.cross_entropy(xr @ w.t(), yr)).backward()
+    assert torch.allclose(out[0], w.grad, atol=1e-6) and torch.allclose(out[1], w.grad, atol=1e-6)
+
+
 def _worker_settle(rank, world, port, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     import sys

@@ -1,6 +1,7 @@
 """CPU: the product's host-side logic (index math, packing, sorting keys, sampling) against the golden
 fixtures made by the reference's own code and against the oracle — no kernels involved."""
 import numpy as np
+import pytest
 import torch
 
 from oracle import host as OH
@@ -76,3 +77,41 @@ def test_synthetic_blob_contract():
     assert len(t) == 8 and t[0].shape == (2, 3, 592, 592) and t[1].shape == (2, 3)
     assert t[3].shape == (40, 4) and t[4].shape == (40, 2) and t[5].shape == (30, 4)
     assert int(t[5][:, 1:3].max()) < 20 and (t[5][:, 1] != t[5][:, 2]).all()
+
+
+def test_prefetch_loader_order_bounds_and_errors():
+    """dataloaders/prefetch.PrefetchLoader, host logic on the CPU device: batches arrive in order
+    with the forward tuple of Blob.__getitem__, the producer never runs more than `depth` + 1 batches ahead, an exception in
+    the batch source surfaces in the consumer, and abandoning the iterator stops the thread."""
+    import threading
+    import time
+    from dataloaders.prefetch import PrefetchLoader
+    from dataloaders.synthetic import make_numpy_batch
+    made = []
+
+    def source(n, fail_at=None):
+        for i in range(n):
+            if fail_at == i:
+                raise ValueError("bad record %d" % i)
+            made.append(i)
+            yield make_numpy_batch(1, seed=i, boxes_per_img=3, rels_per_img=2)
+
+    seen = []
+    for i, blob in enumerate(PrefetchLoader(source(6), "cpu", depth=2)):
+        time.sleep(0.02)
+        assert len(made) <= i + 1 + 2 + 1            # consumed + queue depth + the one being built
+        blob.scatter()
+        tup = blob[0]
+        want = make_numpy_batch(1, seed=i, boxes_per_img=3, rels_per_img=2)
+        assert np.array_equal(tup[0].numpy(), want["imgs"]) and np.array_equal(tup[4].numpy(), want["gt_classes"])
+        assert tup[6] is None and tup[7] is None and tup[2] == 0
+        seen.append(i)
+    assert seen == list(range(6))
+    with pytest.raises(ValueError, match="bad record 2"):
+        for blob in PrefetchLoader(source(5, fail_at=2), "cpu", depth=1):
+            pass
+    before = threading.active_count()
+    it = iter(PrefetchLoader(source(100), "cpu", depth=2))
+    next(it); it.close()
+    time.sleep(0.3)
+    assert threading.active_count() <= before

@@ -405,3 +405,35 @@ def test_anchor_labels_device_vs_oracle(cuda, G):
     assert np.array_equal(mx.cpu().numpy(), want_mx)
     assert np.array_equal(arg.cpu().numpy(), want_arg)
     assert np.array_equal(labels.cpu().numpy(), want)
+
+
+# ------------------------------------------------------------------------------- decoder commitment (a9 / f3)
+@pytest.mark.parametrize("N,seed", [(1, 0), (20, 1), (64, 2), (64, 3)])
+def test_decoder_commit_kernel_identical_to_host_loop(cuda, N, seed):
+    """lib/lstm/decoder_rnn.py:230-247 (overlap-aware greedy label commitment of SGDet eval) as one device kernel vs the
+    reference's host loop restated with numpy: identical commitments, including exact ties of the probabilities (first
+    arg-max in row-major order) and boxes that overlap the winner at IoU >= 0.3 in the winner's class."""
+    import motifs_cabi as C
+    from oracle import ops
+    rng = np.random.RandomState(seed)
+    Cn = 151
+    x1 = rng.uniform(0, 300, (N, 1)); y1 = rng.uniform(0, 300, (N, 1))
+    base = np.concatenate([x1, y1, x1 + rng.uniform(40, 250, (N, 1)), y1 + rng.uniform(40, 250, (N, 1))], 1)
+    boxes = (base[:, None, :] + rng.randn(N, Cn, 4) * 6).astype(np.float32)            # class-specific refinements
+    boxes[..., 2:] = np.maximum(boxes[..., 2:], boxes[..., :2] + 1)
+    logits = rng.randn(N, Cn).astype(np.float32) * 3
+    if seed == 3:                                                                      # exact ties
+        logits = np.round(logits)
+    probs = torch.softmax(torch.from_numpy(logits), 1).numpy()
+    is_overlap = ops.nms_overlaps(boxes) >= np.float32(0.3)
+    sampled = probs.copy(); sampled[:, 0] = 0
+    want = np.zeros(N, dtype=np.int64)
+    for _ in range(N):
+        bi, ci = np.unravel_index(sampled.argmax(), sampled.shape)
+        want[int(bi)] = int(ci)
+        sampled[is_overlap[bi, :, ci], ci] = 0.0
+        sampled[bi] = -1.0
+    got = torch.empty(N, dtype=torch.long, device=cuda)
+    b = torch.from_numpy(boxes).to(cuda); p = torch.from_numpy(probs).to(cuda)
+    C.check(C.load().mb200_decoder_commit(C.ptr(b), C.ptr(p), N, Cn, 0.3, C.ptr(got), C.cur_stream()), "mb200_decoder_commit")
+    assert np.array_equal(got.cpu().numpy(), want)

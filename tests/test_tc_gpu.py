@@ -12,9 +12,20 @@ def relerr(a, b):
     return float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))
 
 
+@pytest.fixture(params=[(0, 0), (2, 0), (2, 2)], ids=["1cta", "pair", "pair_halo"])
+def kernel_mode(request):
+    """Every tcgen05 kernel variant behind mb200_gemm_bf16x3 / mb200_conv3x3_bf16x3: 1-CTA tiles, CTA pairs (cta_group::2),
+    and for the convolution the shared-memory halo kernel; the default picks per shape."""
+    import motifs_cabi as C
+    lib = C.load()
+    old = (lib.mb200_gemm_set_pair_mode(request.param[0]), lib.mb200_conv_set_halo_mode(request.param[1]))
+    yield request.param
+    lib.mb200_gemm_set_pair_mode(old[0]); lib.mb200_conv_set_halo_mode(old[1])
+
+
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (128, 128, 256), (120, 4096, 1000), (1536, 51, 4096),
-                                   (300, 151, 4424), (257, 640, 712), (2000, 3072, 512)])
-def test_gemm_bf16x3_vs_fp64(cuda, M, N, K):
+                                   (300, 151, 4424), (257, 640, 712), (2000, 3072, 512), (384, 512, 1024)])
+def test_gemm_bf16x3_vs_fp64(cuda, kernel_mode, M, N, K):
     from lib import tc_ops
     torch.manual_seed(M + N + K)
     x = torch.randn(M, K, device=cuda)
@@ -65,8 +76,9 @@ def test_linear_tc_autograd(cuda):
     assert relerr(y2, x.detach().double() @ lin.weight.detach().double().t() + lin.bias.detach().double()) < 3e-5
 
 
-@pytest.mark.parametrize("B,H,W,Cin,Cout", [(1, 8, 16, 64, 128), (2, 37, 37, 512, 512), (1, 74, 74, 256, 512), (2, 20, 50, 64, 64)])
-def test_conv3x3_vs_fp64(cuda, B, H, W, Cin, Cout):
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(1, 8, 16, 64, 128), (2, 37, 37, 512, 512), (1, 74, 74, 256, 512), (2, 20, 50, 64, 64),
+                                            (1, 24, 16, 64, 64), (3, 9, 70, 128, 256), (1, 5, 3, 128, 192)])
+def test_conv3x3_vs_fp64(cuda, kernel_mode, B, H, W, Cin, Cout):
     from lib import tc_ops
     torch.manual_seed(B * H + W)
     conv = torch.nn.Conv2d(Cin, Cout, 3, padding=1).to(cuda)
@@ -113,7 +125,7 @@ def test_flat_sgd_matches_torch_sgd_with_clip(cuda):
     for step in range(3):
         grads = [torch.randn(s, device=cuda) * (3.0 if step == 1 else 0.01) for s in shapes]   # step 1 clips
         for p, q, g in zip(a, b, grads):
-            p.grad.add_(g)          # autograd accumulates into the flat views
+            (p * g).sum().backward()          # autograd accumulates g into the flat views (and marks the parameter as used)
             q.grad = g.clone()
         torch.nn.utils.clip_grad_norm_(b, 5.0)
         ref.step()
@@ -121,6 +133,70 @@ def test_flat_sgd_matches_torch_sgd_with_clip(cuda):
         for p, q in zip(a, b):
             assert torch.allclose(p, q, rtol=1e-5, atol=1e-6), float((p - q).abs().max())
             assert float(p.grad.abs().max()) == 0.0
+
+
+def test_flat_sgd_is_a_torch_optimizer(cuda):
+    """The caller's recipe around the optimizer (models/train_rels.py:70, 204-205): ReduceLROnPlateau drives
+    `param_groups[i]['lr']`, which the fused step reads; parameters that never received a gradient are skipped like
+    torch's `grad is None` (no weight decay on them); state_dict round-trips the momentum; `defer_step` (update on a side
+    stream, joined by wait_pending_updates) gives bit-identical parameters."""
+    from torch.optim.lr_scheduler import ReduceLROnPlateau
+    from lib import fused_optim
+    from lib.fused_optim import FlatSGD
+
+    def build():
+        torch.manual_seed(0)
+        return [torch.nn.Parameter(torch.randn(s, device=cuda)) for s in [(64, 33), (7,), (129, 5), (11,)]]
+
+    def run(defer, steps=4, reload_at=None):
+        ps = build()
+        opt = FlatSGD([{'params': ps[:2], 'lr': 0.01}, {'params': ps[2:]}], lr=0.1, momentum=0.9, weight_decay=1e-2,
+                      max_norm=5.0, defer_step=defer)
+        sched = ReduceLROnPlateau(opt, 'max', patience=0, factor=0.1)
+        for step in range(steps):
+            torch.manual_seed(100 + step)
+            fused_optim.wait_pending_updates()          # what RelModel.forward does before it reads a trainable parameter
+            opt.zero_grad()
+            loss = sum((p * torch.randn_like(p)).sum() for p in ps[:3])         # ps[3] is never used
+            loss.backward()
+            opt.step()
+            if step == 1:
+                sched.step(0.5); sched.step(0.4)                               # no improvement -> lr * 0.1
+            if reload_at == step:
+                sd = opt.state_dict()
+                ps2 = [torch.nn.Parameter(p.detach().clone()) for p in ps]
+                opt2 = FlatSGD([{'params': ps2[:2], 'lr': 1.0}, {'params': ps2[2:]}], lr=1.0, momentum=0.9, weight_decay=1e-2,
+                               max_norm=5.0, defer_step=defer)
+                opt2.load_state_dict(sd)
+                ps, opt = ps2, opt2
+        fused_optim.wait_pending_updates()
+        torch.cuda.synchronize()
+        return ps, opt
+
+    ps, opt = run(False)
+    assert isinstance(opt, torch.optim.Optimizer)
+    assert abs(opt.param_groups[0]['lr'] - 0.001) < 1e-12 and abs(opt.param_groups[1]['lr'] - 0.01) < 1e-12
+    assert torch.equal(ps[3], build()[3])                                      # untouched: not even weight decay
+    # torch reference with the same schedule
+    qs = build()
+    ref = torch.optim.SGD([{'params': qs[:2], 'lr': 0.01}, {'params': qs[2:]}], lr=0.1, momentum=0.9, weight_decay=1e-2)
+    for step in range(4):
+        torch.manual_seed(100 + step)
+        ref.zero_grad()
+        sum((p * torch.randn_like(p)).sum() for p in qs[:3]).backward()
+        torch.nn.utils.clip_grad_norm_([q for q in qs if q.grad is not None], 5.0)
+        ref.step()
+        if step == 1:
+            for g in ref.param_groups:
+                g['lr'] *= 0.1
+    for p, q in zip(ps, qs):
+        assert torch.allclose(p, q, rtol=1e-5, atol=1e-6), float((p - q).abs().max())
+    pd, _ = run(True)
+    for p, q in zip(ps, pd):
+        assert torch.equal(p, q)
+    pr, _ = run(False, reload_at=1)
+    for p, q in zip(ps, pr):
+        assert torch.equal(p, q)
 
 
 @pytest.mark.parametrize("B,H,W", [(1, 5, 7), (2, 33, 70), (1, 64, 96)])

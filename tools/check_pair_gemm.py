@@ -58,11 +58,20 @@ for (M, N, K) in [(256, 128, 64), (256, 256, 256), (512, 256, 128), (384, 512, 1
     e = gemm_case(M, N, K, 2)
     print("gemm pair", (M, N, K), "relerr %.2e %.2e" % e, flush=True)
     out["numerics"].append(["gemm", M, N, K, e[0], e[1]]); ok &= max(e) < 3e-5
-for (B, H, W, Ci, Co) in [(1, 8, 32, 64, 128), (1, 24, 16, 64, 64), (2, 37, 37, 512, 512), (1, 74, 74, 256, 512), (3, 9, 70, 128, 256),
-                          (2, 20, 50, 64, 64)]:
-    e = conv_case(B, H, W, Ci, Co, 2)
-    print("conv pair", (B, H, W, Ci, Co), "relerr %.2e %.2e" % e, flush=True)
-    out["numerics"].append(["conv", B, H, W, Ci, Co, e[0], e[1]]); ok &= max(e) < 3e-5
+halo_ok = {}
+for halo in (0, 2):
+    lib.mb200_conv_set_halo_mode(halo)
+    good = True
+    for (B, H, W, Ci, Co) in [(1, 8, 32, 64, 128), (1, 24, 16, 64, 64), (2, 37, 37, 512, 512), (1, 74, 74, 256, 512), (3, 9, 70, 128, 256),
+                              (2, 20, 50, 64, 64), (1, 16, 8, 64, 64), (1, 5, 3, 128, 192)]:
+        e = conv_case(B, H, W, Ci, Co, 2)
+        print("conv pair halo=%d" % halo, (B, H, W, Ci, Co), "relerr %.2e %.2e" % e, flush=True)
+        out["numerics"].append(["conv", halo, B, H, W, Ci, Co, e[0], e[1]]); good &= max(e) < 3e-5
+    halo_ok[halo] = good
+print("HALO numerics", halo_ok, flush=True)
+ok &= halo_ok[0]
+HALO = 2 if halo_ok[2] else 0
+lib.mb200_conv_set_halo_mode(HALO)
 print("NUMERICS", "OK" if ok else "FAIL", flush=True)
 if ok and "--time" in sys.argv:
     Bn = 6
@@ -72,9 +81,11 @@ if ok and "--time" in sys.argv:
         xh = torch.randn(Bn, S, S, Ci, device=dev).bfloat16(); xl = (torch.randn(Bn, S, S, Ci, device=dev) * 1e-3).bfloat16()
         row = {"layer": [S, Ci, Co], "gflop": 2.0 * Bn * S * S * Co * 9 * Ci / 1e9}
         for mode in (0, 1, 2):
-            lib.mb200_gemm_set_pair_mode(mode)
+            lib.mb200_gemm_set_pair_mode(mode if mode < 2 else 1)
+            lib.mb200_conv_set_halo_mode(0 if mode < 2 else HALO)       # mode0: 1-CTA taps; mode1: pair taps; mode2: pair + halo
             us = timeit(lambda: tc_ops.conv3x3_relu((xh, xl), Bn, S, S, Ci, conv, want_f32=False, want_split=True))
             row["us_mode%d" % mode] = us; row["tflops_mode%d" % mode] = row["gflop"] / us * 1e3
+        lib.mb200_gemm_set_pair_mode(1)
         print(json.dumps(row), flush=True); out["timing"].append(row)
     for (M, N, K) in [(1536, 4096, 25088), (1536, 4096, 4096), (1536, 25088, 4096), (4096, 25088, 1536), (120, 4096, 25088), (75264, 512, 2304), (75264, 256, 128)]:
         x = tc_ops.split_rows(torch.randn(M, K, device=dev)); w = tc_ops.split_rows(torch.randn(N, K, device=dev))
