@@ -249,6 +249,11 @@ int mb200_sgd_momentum_clip(float* params, float* grads, float* momentum_buf, lo
 int mb200_sgd_momentum_clip_scaled(float* params, float* grads, float* momentum_buf, long long n, float lr, float momentum,
                                    float weight_decay, const float* total_norm_dev, float max_norm, float grad_scale,
                                    int first_step, int zero_grad, cudaStream_t stream);
+/* Same, and the bf16 (hi, lo) pair of every UPDATED parameter is written to hi[i], lo[i] (same flat index; 8-byte aligned):
+ * for weight matrices whose row length is a multiple of 64 these ARE the K-major GEMM operands of mb200_gemm_bf16x3. */
+int mb200_sgd_momentum_clip_split(float* params, float* grads, float* momentum_buf, void* hi, void* lo, long long n, float lr,
+                                  float momentum, float weight_decay, const float* total_norm_dev, float max_norm,
+                                  float grad_scale, int first_step, int zero_grad, cudaStream_t stream);
 
 #ifdef __cplusplus
 }

@@ -5,10 +5,16 @@
 // no nesterov) — with ONE pass over (param, grad, momentum): 20 bytes per parameter instead of
 // the ~44 the foreach kernels move, and the gradient is zeroed in the same pass.
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace {
 
+// SPLIT: also emit the bf16 (hi, lo) pair of the UPDATED parameter at the same flat index — for every weight matrix whose
+// row length is a multiple of 64 that IS the K-major operand layout of the tcgen05 GEMM, so the per-step re-split of the
+// trainable weights (fc6 / fc7 copies: 2.2 GB of traffic, 0.3 ms on the compute stream) rides along with the update.
+template <bool SPLIT>
 __global__ void sgd_momentum_clip_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ buf,
+                                         __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
                                          long long n, float lr, float momentum, float weight_decay,
                                          const float* __restrict__ total_norm, float max_norm, float grad_scale,
                                          int first_step, int zero_grad) {
@@ -48,6 +54,13 @@ __global__ void sgd_momentum_clip_kernel(float* __restrict__ p, float* __restric
         }
         __stcs(p4 + i, pv[u]); __stcs(b4 + i, bv[u]);
         if (zero_grad) __stcs(g4 + i, make_float4(0.f, 0.f, 0.f, 0.f));
+        if (SPLIT) {
+          __nv_bfloat16 h[4], l[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) tc::split_bf16(pp[k], h[k], l[k]);
+          *(uint2*)(hi + 4 * i) = *(const uint2*)h;
+          *(uint2*)(lo + 4 * i) = *(const uint2*)l;
+        }
       }
     }
   }
@@ -58,6 +71,7 @@ __global__ void sgd_momentum_clip_kernel(float* __restrict__ p, float* __restric
     buf[i] = b;
     p[i] = fmaf(-lr, b, p[i]);
     if (zero_grad) g[i] = 0.f;
+    if (SPLIT) tc::split_bf16(p[i], hi[i], lo[i]);
   }
 }
 
@@ -115,9 +129,25 @@ extern "C" int mb200_sgd_momentum_clip_scaled(float* params, float* grads, float
   if (n <= 0) return MB200_OK;
   if ((((uintptr_t)params) | ((uintptr_t)grads) | ((uintptr_t)momentum_buf)) & 15) return MB200_ERR_ARG;
   const int blocks = (int)min((long long)kNumSMs * 8, (n / 4 + 255) / 256 + 1);
-  sgd_momentum_clip_kernel<<<blocks, 256, 0, stream>>>(params, grads, momentum_buf, n, lr, momentum, weight_decay,
-                                                       total_norm_dev, max_norm, grad_scale, first_step, zero_grad);
+  sgd_momentum_clip_kernel<false><<<blocks, 256, 0, stream>>>(params, grads, momentum_buf, nullptr, nullptr, n, lr, momentum,
+                                                              weight_decay, total_norm_dev, max_norm, grad_scale, first_step,
+                                                              zero_grad);
   MB200_CHECK_LAUNCH("mb200_sgd_momentum_clip");
+  return MB200_OK;
+}
+
+extern "C" int mb200_sgd_momentum_clip_split(float* params, float* grads, float* momentum_buf, void* hi, void* lo, long long n,
+                                             float lr, float momentum, float weight_decay, const float* total_norm_dev,
+                                             float max_norm, float grad_scale, int first_step, int zero_grad,
+                                             cudaStream_t stream) {
+  if (n <= 0) return MB200_OK;
+  if ((((uintptr_t)params) | ((uintptr_t)grads) | ((uintptr_t)momentum_buf)) & 15) return MB200_ERR_ARG;
+  if ((((uintptr_t)hi) | ((uintptr_t)lo)) & 7) return MB200_ERR_ARG;
+  const int blocks = (int)min((long long)kNumSMs * 8, (n / 4 + 255) / 256 + 1);
+  sgd_momentum_clip_kernel<true><<<blocks, 256, 0, stream>>>(params, grads, momentum_buf, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo,
+                                                             n, lr, momentum, weight_decay, total_norm_dev, max_norm,
+                                                             grad_scale, first_step, zero_grad);
+  MB200_CHECK_LAUNCH("mb200_sgd_momentum_clip_split");
   return MB200_OK;
 }
 

@@ -8,6 +8,7 @@ import torch
 
 from config import BG_THRESH_HI, BG_THRESH_LO, FG_FRACTION, ROIS_PER_IMG
 from lib.fpn.box_utils import bbox_overlaps
+from lib.pytorch_misc import to_device_async
 
 
 def _sel_inds(max_overlaps, fg_thresh=0.5, fg_rois_per_image=128, rois_per_image=256, rng=npr):
@@ -47,7 +48,7 @@ def proposal_assignments_det(rpn_rois, gt_boxes, gt_classes, image_offset, fg_th
         keep_np, num_fg = _sel_inds(max_overlaps.cpu().numpy(), fg_thresh, fg_rois_per_image, ROIS_PER_IMG, rng)
         if keep_np.size == 0:
             continue
-        keep = torch.as_tensor(keep_np, dtype=torch.long, device=dev)
+        keep = to_device_async(keep_np, dev, torch.long)
         labels_ = gt_classes[:, 1][gt_assignment[keep]].clone()
         if num_fg < labels_.size(0):
             labels_[num_fg:] = 0

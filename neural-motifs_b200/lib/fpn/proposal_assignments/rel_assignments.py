@@ -13,6 +13,7 @@ import torch
 
 from config import REL_FG_FRACTION
 from lib.fpn.box_intersections_cpu.bbox import bbox_overlaps_cuda
+from lib.pytorch_misc import to_device_async
 
 
 def rel_assignments(im_inds, rpn_rois, roi_gtlabels, gt_boxes, gt_classes, gt_rels, image_offset, fg_thresh=0.5,
@@ -86,4 +87,4 @@ def rel_assignments(im_inds, rpn_rois, roi_gtlabels, gt_boxes, gt_classes, gt_re
         allr = allr[np.lexsort((allr[:, 1], allr[:, 0]))]
         out.append(np.column_stack((im * np.ones(allr.shape[0], dtype=np.int64), allr)))
         num_box_seen += n
-    return torch.as_tensor(np.concatenate(out, 0), dtype=torch.long, device=dev)
+    return to_device_async(np.concatenate(out, 0), dev, torch.long)

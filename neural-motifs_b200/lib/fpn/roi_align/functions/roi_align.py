@@ -12,11 +12,17 @@ from torch.autograd import Function
 import motifs_cabi as _c
 
 
+_SCALE_CACHE = {}
+
+
 def normalize_rois(rois, feat_h, feat_w, spatial_scale):
     """roi_align.py:20-31 — corners divided by (W-1)/scale, (H-1)/scale (fp32)."""
     height = (feat_h - 1) / spatial_scale
     width = (feat_w - 1) / spatial_scale
-    scale = rois.new_tensor([1.0, width, height, width, height])
+    key = (rois.device, rois.dtype, feat_h, feat_w, spatial_scale)
+    scale = _SCALE_CACHE.get(key)
+    if scale is None:       # built once: `new_tensor(list)` is a pageable H2D copy, which stalls the host behind the stream
+        scale = _SCALE_CACHE[key] = rois.new_tensor([1.0, width, height, width, height])
     return (rois / scale).contiguous()
 
 

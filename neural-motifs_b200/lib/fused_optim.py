@@ -57,6 +57,7 @@ class FlatGroup(object):
         self.flat_p = torch.zeros(n, device=dev, dtype=torch.float32)
         self.flat_g = torch.zeros(n, device=dev, dtype=torch.float32)
         self.flat_m = torch.zeros(n, device=dev, dtype=torch.float32)
+        self.flat_hi = self.flat_lo = None          # bf16 pairs of the parameters, written by the fused update (presplit)
         self.touched = [False] * len(params)
         with torch.no_grad():
             for p, o in zip(params, offs):
@@ -95,7 +96,7 @@ class FlatSGD(torch.optim.Optimizer):
     default). momentum / weight_decay / max_norm shared (train_rels.py:66,145)."""
 
     def __init__(self, groups, lr=None, momentum=0.9, weight_decay=1e-4, max_norm=5.0, overlap_comm=True,
-                 chunk_bytes=128 << 20, defer_step=False):
+                 chunk_bytes=128 << 20, defer_step=False, presplit=True):
         pgs = []
         for g in groups:
             if isinstance(g, dict):
@@ -126,6 +127,13 @@ class FlatSGD(torch.optim.Optimizer):
         self._stream = torch.cuda.Stream(self._device) if self._defer else None
         self._pending_ev = None
         self._reduced = False
+        # presplit: the update kernel also writes the bf16 (hi, lo) pair of every updated parameter (+2 x 2 B per parameter);
+        # weight matrices whose rows are a multiple of 64 long hand those views to lib/tc_ops as their GEMM operand
+        self._presplit = bool(presplit) and self._device.type == "cuda"
+        if self._presplit:
+            for g in self.groups:
+                g.flat_hi = torch.zeros(g.n, device=self._device, dtype=torch.bfloat16)
+                g.flat_lo = torch.zeros(g.n, device=self._device, dtype=torch.bfloat16)
         self._acc = torch.zeros(1, dtype=torch.float64, device=self._device)
         self._total = torch.zeros(1, dtype=torch.float32, device=self._device)
         # One hook per parameter. (1) It marks the parameter's flat gradient as touched by autograd, which ends
@@ -221,11 +229,18 @@ class FlatSGD(torch.optim.Optimizer):
             lr = float(pg['lr'])
             for a, b in g.touched_ranges():
                 with torch.cuda.device(g.flat_p.device):
-                    rc = lib.mb200_sgd_momentum_clip_scaled(
-                        _c.ptr(g.flat_p[a:b]), _c.ptr(g.flat_g[a:b]), _c.ptr(g.flat_m[a:b]), b - a, lr,
-                        float(pg.get('momentum', self.momentum)), float(pg.get('weight_decay', self.weight_decay)),
-                        _c.ptr(self._total), float(self.max_norm), float(inv), first, 1, _c.cur_stream())
-                _c.check(rc, "mb200_sgd_momentum_clip_scaled")
+                    if self._presplit:
+                        rc = lib.mb200_sgd_momentum_clip_split(
+                            _c.ptr(g.flat_p[a:b]), _c.ptr(g.flat_g[a:b]), _c.ptr(g.flat_m[a:b]), _c.ptr(g.flat_hi[a:b]),
+                            _c.ptr(g.flat_lo[a:b]), b - a, lr, float(pg.get('momentum', self.momentum)),
+                            float(pg.get('weight_decay', self.weight_decay)), _c.ptr(self._total), float(self.max_norm),
+                            float(inv), first, 1, _c.cur_stream())
+                    else:
+                        rc = lib.mb200_sgd_momentum_clip_scaled(
+                            _c.ptr(g.flat_p[a:b]), _c.ptr(g.flat_g[a:b]), _c.ptr(g.flat_m[a:b]), b - a, lr,
+                            float(pg.get('momentum', self.momentum)), float(pg.get('weight_decay', self.weight_decay)),
+                            _c.ptr(self._total), float(self.max_norm), float(inv), first, 1, _c.cur_stream())
+                _c.check(rc, "mb200_sgd_momentum_clip")
         self._reduced = False
 
     @torch.no_grad()
@@ -254,6 +269,12 @@ class FlatSGD(torch.optim.Optimizer):
             for p in g.params:
                 p._mb200_direct.reset()
         tc_ops.bump_weight_epoch()       # raw-pointer update: invalidate the bf16 split caches
+        if self._presplit:               # ... and hand over the splits the update kernel has just written
+            for g in self.groups:
+                for i, (p, o) in enumerate(zip(g.params, g.offs)):
+                    if g.touched[i] and p.dim() == 2 and p.size(1) % 64 == 0:
+                        n = p.numel()
+                        tc_ops.preset_rows_split(p, g.flat_hi[o:o + n].view_as(p), g.flat_lo[o:o + n].view_as(p))
         return None if self._defer else self._total
 
     def total_norm(self):

@@ -18,6 +18,7 @@ from lib.fpn.box_utils import nms_overlaps
 from lib.word_vectors import obj_edge_vectors
 from lib.lstm.highway_lstm_cuda.alternating_highway_lstm import block_orthogonal, _HighwayLayerFunction
 from lib import tc_ops
+from lib.pytorch_misc import to_device_async
 
 
 def get_dropout_mask(dropout_probability, tensor_for_masking):
@@ -87,14 +88,14 @@ class DecoderRNN(torch.nn.Module):
         t_of = np.repeat(np.arange(T), bl)
         b_of = np.arange(N) - off[t_of]
         src = np.where(t_of > 0, off[np.maximum(t_of - 1, 0)] + b_of, -1)       # packed position of (t-1, b)
-        src_d = torch.as_tensor(src, device=dev)
+        src_d = to_device_async(src, dev)
         prev_idx = torch.where(src_d >= 0, labels[src_d.clamp_min(0)] + 1, torch.zeros_like(src_d))
         x = torch.cat((sequence_tensor, self.obj_embed(prev_idx)), 1)
         P = tc_ops.linear_tc(x, self.input_linearity.weight, self.input_linearity.bias)          # [N,6H]
-        flat = torch.as_tensor(t_of * B + b_of, device=dev)
+        flat = to_device_async(t_of * B + b_of, dev)
         P_pad = torch.zeros(T * B, 6 * H, device=dev, dtype=torch.float32).index_copy(0, flat, P).view(T, B, 6 * H)
         lengths = (bl[None, :] > np.arange(B)[:, None]).sum(1)                                     # per sequence
-        lengths_dev = torch.as_tensor(lengths, device=dev, dtype=torch.int32)
+        lengths_dev = to_device_async(lengths, dev, torch.int32)
         if dropout_mask is None or not self.training:
             dropout_mask = torch.ones(B, H, device=dev, dtype=torch.float32)
         wh = self.state_linearity.weight.t()          # [H,5H] view; the Function makes it contiguous
@@ -125,7 +126,7 @@ class DecoderRNN(torch.nn.Module):
             commit[int(box_ind)] = int(cls_ind)
             sampled[is_overlap[box_ind, :, cls_ind], cls_ind] = 0.0
             sampled[box_ind] = -1.0
-        return torch.as_tensor(commit, device=dev)
+        return to_device_async(commit, dev)
 
     def forward(self, inputs, initial_state=None, labels=None, boxes_for_nms=None, dropout_mask=None, labels_all_fg=None):
         """`labels_all_fg` (superset of the reference signature): whether every label is foreground, when the caller

@@ -157,7 +157,8 @@ class AlternatingHighwayLSTM(torch.nn.Module):
                 keep = 1 - self.recurrent_dropout_probability
                 dropout_weights.bernoulli_(keep).div_(keep)
         dropout_weights = dropout_weights.to(dev).contiguous()
-        lengths_dev = lengths.to(device=dev, dtype=torch.int32)
+        from lib.pytorch_misc import to_device_async
+        lengths_dev = to_device_async(lengths, dev, torch.int32)       # (pageable H2D copies stall the host)
         save_gates = torch.is_grad_enabled() and (padded.requires_grad or self.weight.requires_grad
                                                   or self.bias.requires_grad)
         from lib import tc_ops

@@ -39,6 +39,21 @@ def gather_nd(x, index):
     return x.reshape(-1, dim)[sel]
 
 
+def to_device_async(a, device, dtype=None):
+    """numpy array / list / CPU tensor -> tensor on `device` WITHOUT stalling the host. `torch.as_tensor(a, device=cuda)`
+    copies from pageable memory: the call is host-synchronous and stream-ordered, i.e. the host waits until everything
+    already queued on the stream (the whole backbone) has run — round 2's GPU trace showed the forward after the backbone
+    host-bound for that reason alone (3.6 ms of idle in 6 ms). Here the data goes through a pinned staging tensor
+    (PyTorch's caching host allocator) and an asynchronous copy."""
+    t = torch.as_tensor(a)
+    if dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)
+    device = torch.device(device)
+    if device.type != "cuda":
+        return t.to(device)
+    return t.pin_memory().to(device, non_blocking=True)
+
+
 def image_segments(im_inds, host=None):
     """Runs of equal image index as a python list [(image, start, end)]. One small D2H read of the
     [N] index vector (the reference does the same, pytorch_misc.py:279) unless the caller already holds
@@ -73,7 +88,7 @@ def random_choose(tensor, num, rng=np.random):
     if num_choose == tensor.size(0):
         return tensor
     rand_idx = rng.choice(tensor.size(0), size=num, replace=False)
-    rand_idx = torch.as_tensor(rand_idx, dtype=torch.long, device=tensor.device)
+    rand_idx = to_device_async(rand_idx, tensor.device, torch.long)
     return tensor[rand_idx].contiguous()
 
 

@@ -28,7 +28,7 @@ from lib.get_union_boxes import UnionBoxesAndFeats
 from lib.lstm.decoder_rnn import DecoderRNN
 from lib.lstm.highway_lstm_cuda.alternating_highway_lstm import AlternatingHighwayLSTM
 from lib.object_detector import ObjectDetector, gather_res, load_vgg, run_classifier
-from lib.pytorch_misc import transpose_packed_sequence_inds, to_onehot, arange, image_segments, Flattener
+from lib.pytorch_misc import transpose_packed_sequence_inds, to_onehot, arange, image_segments, Flattener, to_device_async
 from lib.sparse_targets import FrequencyBias
 from lib.surgery import filter_dets
 from lib.word_vectors import obj_edge_vectors
@@ -57,8 +57,8 @@ def _sort_by_score(im_inds, scores, host=None):
         lengths.append(e - s)
     lengths = sorted(lengths, reverse=True)
     inds, ls_transposed = transpose_packed_sequence_inds(lengths)
-    inds = torch.as_tensor(inds, dtype=torch.long, device=im_inds.device)
-    rpi = torch.as_tensor(rois_per_image, device=im_inds.device)
+    inds = to_device_async(inds, im_inds.device, torch.long)
+    rpi = to_device_async(rois_per_image, im_inds.device)
     roi_order = scores - 2 * rpi[im_inds]
     # stable: objects whose keys tie exactly (PredCls ordered by confidence: every confidence is 1.0) keep their input
     # order, as in the oracle; an unstable sort leaves the order to the backend (CPU and CUDA differ)
@@ -146,7 +146,7 @@ class LinearizedContext(nn.Module):
         elif self.order == 'confidence':
             scores = confidence
         elif self.order == 'random':
-            scores = torch.as_tensor(np.random.rand(batch_idx.size(0)), dtype=torch.float32, device=batch_idx.device)
+            scores = to_device_async(np.random.rand(batch_idx.size(0)), batch_idx.device, torch.float32)
         elif self.order == 'leftright':
             centers = cxcywh[:, 0]
             scores = centers / (centers.max() + 1)

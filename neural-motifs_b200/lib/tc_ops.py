@@ -188,9 +188,19 @@ def _version_of(t, shape):
     return (t.data_ptr(), t._version, tuple(shape), WEIGHT_EPOCH if t.requires_grad else 0, LOAD_EPOCH)
 
 
+def preset_rows_split(param, hi, lo):
+    """An optimizer that has just written the parameter AND its bf16 pair (lib/fused_optim.FlatSGD, presplit) hands the pair
+    over: valid until the next weight / load epoch. `hi`, `lo`: [N, K] bf16 views with K % 64 == 0."""
+    param._mb200_presplit = ((WEIGHT_EPOCH, LOAD_EPOCH, param.data_ptr()), SplitMat(hi, lo, param.size(0), param.size(1), param.size(1)))
+
+
 def _cached(param, kind, maker):
     """Split copies of a parameter are rebuilt only when the parameter changes (optimizer steps bump `_version`
     or the weight epoch); frozen weights are split once per load."""
+    if kind == "rows":
+        ps = getattr(param, "_mb200_presplit", None)
+        if ps is not None and ps[0] == (WEIGHT_EPOCH, LOAD_EPOCH, param.data_ptr()):
+            return ps[1]
     owner = param._base if param._base is not None else param     # views (w.view(out, -1)) are temporaries: key on the base
     key = (id(owner), kind) if owner is param else \
         (id(owner), kind, param.storage_offset(), tuple(param.shape), tuple(param.stride()))

@@ -199,6 +199,34 @@ def test_flat_sgd_is_a_torch_optimizer(cuda):
         assert torch.equal(p, q)
 
 
+def test_flat_sgd_presplit_hands_over_identical_operands(cuda):
+    """The fused update also writes the bf16 (hi, lo) pair of the updated parameters; for matrices with K % 64 == 0
+    lib/tc_ops takes them as the GEMM operand instead of re-splitting: they must equal split_rows(param) bit for bit, stop
+    being used after a foreign write + invalidate_all(), and never be offered for other shapes."""
+    from lib import tc_ops
+    from lib.fused_optim import FlatSGD
+    torch.manual_seed(0)
+    w = torch.nn.Parameter(torch.randn(96, 128, device=cuda)); v = torch.nn.Parameter(torch.randn(40, 100, device=cuda))
+    b = torch.nn.Parameter(torch.randn(128, device=cuda))
+    opt = FlatSGD([([w, v, b], 0.1)], momentum=0.9, weight_decay=1e-4, max_norm=5.0)
+    for step in range(2):
+        opt.zero_grad()
+        ((w * 2).sum() + v.pow(2).sum() + b.sum()).backward()
+        opt.step()
+        got = tc_ops.weight_split(w)
+        assert got is w._mb200_presplit[1]                                    # the handed-over views, no kernel
+        want = tc_ops.split_rows(w.detach())
+        assert torch.equal(got.hi, want.hi) and torch.equal(got.lo, want.lo)
+        assert not hasattr(v, "_mb200_presplit") and not hasattr(b, "_mb200_presplit")      # K = 100: needs padding
+        gv = tc_ops.weight_split(v); wv = tc_ops.split_rows(v.detach())
+        assert torch.equal(gv.hi, wv.hi) and torch.equal(gv.lo, wv.lo)
+    with torch.no_grad():
+        w.data.mul_(2.0)
+    tc_ops.invalidate_all()
+    got = tc_ops.weight_split(w); want = tc_ops.split_rows(w.detach())
+    assert got is not w._mb200_presplit[1] and torch.equal(got.hi, want.hi)
+
+
 @pytest.mark.parametrize("B,H,W", [(1, 5, 7), (2, 33, 70), (1, 64, 96)])
 def test_stem_conv_vs_fp64(cuda, B, H, W):
     """csrc/stem.cu: conv1_1 (3->64) + bias + ReLU, exact fp32 FMAs; output is the NHWC bf16 pair."""
