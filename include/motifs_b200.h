@@ -233,6 +233,16 @@ int mb200_gemm_set_pair_mode(int mode);
 /* 3x3 convolution kernel: 0 = tap-by-tap shifted TMA boxes, 1 = per layer (default), 2 = shared-memory halo staging always. */
 int mb200_conv_set_halo_mode(int mode);
 
+/* Highway-LSTM recurrence of ONE layer on the tensor cores (csrc/lstm_tc.cu; large batches — BASELINE configs[4]): same
+ * contract as mb200_highway_lstm_layer_forward. Wt_hi / Wt_lo: W_h as bf16 pairs [H/16 * 80, H], K contiguous, row
+ * (s*80 + g*16 + u) = column (g*H + 16 s + u) of W_h [H,5H]; hb_hi / hb_lo: [T+1,B,H] bf16 scratch, ZERO on entry (the
+ * bf16 pair of the hidden state). mb200_highway_lstm_tc_supported: H % 64 == 0, weight slice fits shared memory. */
+int mb200_highway_lstm_tc_supported(int hiddenSize, int miniBatch);
+int mb200_highway_lstm_layer_forward_tc(int hiddenSize, int miniBatch, int seqLength, int dir, const float* P,
+                                        const void* Wt_hi, const void* Wt_lo, const float* bias, const float* dropout,
+                                        float* h, float* c, void* hb_hi, void* hb_lo, float* gates,
+                                        const int* lengths_dev, cudaStream_t stream);
+
 /* *acc += sum_i x[i]^2 (double accumulator on the device, caller zeroes it): the global gradient norm of
  * clip_grad_norm (lib/pytorch_misc.py:416-459) as one pass per flat buffer. x 16-byte aligned. */
 int mb200_sumsq_accum(const float* x, long long n, double* acc, cudaStream_t stream);

@@ -420,15 +420,20 @@ __global__ void colsum_accum_kernel(const float* __restrict__ in, int rows, int 
 size_t fwd_smem_bytes(int H, int B) { return ((size_t)H * 5 * kUJ + (size_t)kBTf * (H + 4) + B) * 4; }
 size_t bwd_smem_bytes(int H, int B) { return ((size_t)kUJ * 5 * H + (size_t)kBTb * (5 * H + 4) + B) * 4; }
 
+// The barrier words are __device__ globals: one instance PER DEVICE, so the address is cached per device (a process that
+// drives a second GPU must not spin on the first one's counter). One counter per direction and device: launches of the
+// same direction are serialised by the single compute stream this library runs on (they must not overlap on two streams).
 unsigned int* barrier_ptr(int which, cudaStream_t stream) {
-  static unsigned int* base = nullptr;
-  if (!base) {
+  static unsigned int* base[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  if (!base[dev]) {
     void* p = nullptr;
     if (cudaGetSymbolAddress(&p, g_lstm_barrier) != cudaSuccess) return nullptr;
-    base = (unsigned int*)p;
+    base[dev] = (unsigned int*)p;
   }
-  cudaMemsetAsync(base + which, 0, sizeof(unsigned int), stream);
-  return base + which;
+  cudaMemsetAsync(base[dev] + which, 0, sizeof(unsigned int), stream);
+  return base[dev] + which;
 }
 
 int check_coop(const void* fn, int grid, size_t smem) {

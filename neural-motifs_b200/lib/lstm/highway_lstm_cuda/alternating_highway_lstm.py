@@ -36,13 +36,30 @@ def block_orthogonal(tensor, split_sizes, gain=1.0):
     return tensor
 
 
+TC_MIN_BATCH = 48          # below this the recurrence is latency-bound and the SIMT kernel (csrc/lstm.cu) is faster
+TC_RECURRENCE = __import__("os").environ.get("MOTIFS_LSTM_TC", "1") == "1"
+
+
+def use_tensor_core_recurrence(H, B):
+    return TC_RECURRENCE and B >= TC_MIN_BATCH and bool(_c.load().mb200_highway_lstm_tc_supported(H, B))
+
+
+def _recurrent_weight_slices(wh):
+    """W_h [H,5H] fp32 -> the K-major bf16 pair the tensor-core recurrence keeps in shared memory: [H/16 * 80, H] with row
+    (s*80 + g*16 + u) = column (g*H + 16 s + u) — slice s holds the five gates of hidden units 16 s .. 16 s + 15."""
+    from lib import tc_ops
+    H = wh.size(0)
+    wt = wh.t().reshape(5, H // 16, 16, H).permute(1, 0, 2, 3).reshape(5 * H, H).contiguous()
+    return tc_ops.split_rows(wt)
+
+
 class _HighwayLayerFunction(Function):
     """One layer of the recurrence on the persistent kernel (csrc/lstm.cu). P [T,B,6H] is the hoisted
     input projection (a tcgen05 GEMM, lib/tc_ops.py); the kernel overwrites it in place with the six
     gate activations, which is what backward needs (elementWise_fp/bp, highway_lstm_kernel.cu:46-160)."""
 
     @staticmethod
-    def forward(ctx, P, Wh, bias, dropout, lengths_dev, direction, save_gates, base=None):
+    def forward(ctx, P, Wh, bias, dropout, lengths_dev, direction, save_gates, base=None, tc_tag=None):
         _c.require_cuda(P, Wh, bias, dropout, lengths_dev)
         P = P.contiguous()
         Wh = Wh.contiguous()
@@ -53,12 +70,28 @@ class _HighwayLayerFunction(Function):
         h = torch.zeros(T + 1, B, H, device=dev, dtype=torch.float32)
         c = torch.zeros(T + 1, B, H, device=dev, dtype=torch.float32)
         lib = _c.load()
-        with torch.cuda.device(dev):
-            rc = lib.mb200_highway_lstm_layer_forward(H, B, T, direction, _c.ptr(P), _c.ptr(Wh), _c.ptr(bias),
-                                                      _c.ptr(dropout), _c.ptr(h), _c.ptr(c),
-                                                      _c.ptr(P) if save_gates else None, _c.ptr(lengths_dev),
-                                                      _c.cur_stream())
-        _c.check(rc, "mb200_highway_lstm_layer_forward")
+        if use_tensor_core_recurrence(H, B):
+            # large batches: the per-step [B,H] x [H,5H] product on tcgen05 (csrc/lstm_tc.cu); h / c / gates come out in
+            # the same layout, so backward is unchanged
+            from lib import tc_ops
+            wt = tc_ops._cached_view(base, (tc_tag, "wh_tc"), Wh, _recurrent_weight_slices) if base is not None and tc_tag is not None \
+                else _recurrent_weight_slices(Wh.detach())
+            hb_hi = torch.zeros(T + 1, B, H, device=dev, dtype=torch.bfloat16)
+            hb_lo = torch.zeros(T + 1, B, H, device=dev, dtype=torch.bfloat16)
+            with torch.cuda.device(dev):
+                rc = lib.mb200_highway_lstm_layer_forward_tc(H, B, T, direction, _c.ptr(P), _c.ptr(wt.hi), _c.ptr(wt.lo),
+                                                             _c.ptr(bias), _c.ptr(dropout), _c.ptr(h), _c.ptr(c),
+                                                             _c.ptr(hb_hi), _c.ptr(hb_lo),
+                                                             _c.ptr(P) if save_gates else None, _c.ptr(lengths_dev),
+                                                             _c.cur_stream())
+            _c.check(rc, "mb200_highway_lstm_layer_forward_tc")
+        else:
+            with torch.cuda.device(dev):
+                rc = lib.mb200_highway_lstm_layer_forward(H, B, T, direction, _c.ptr(P), _c.ptr(Wh), _c.ptr(bias),
+                                                          _c.ptr(dropout), _c.ptr(h), _c.ptr(c),
+                                                          _c.ptr(P) if save_gates else None, _c.ptr(lengths_dev),
+                                                          _c.cur_stream())
+            _c.check(rc, "mb200_highway_lstm_layer_forward")
         ctx.direction = direction
         ctx.have_gates = save_gates
         ctx.base = base            # the flat parameter Wh is a view of (direct gradient writes, tc_ops.direct_grad_target)
@@ -105,7 +138,7 @@ class _HighwayLayerFunction(Function):
                 dWh = torch.zeros_like(Wh)
         if ctx.needs_input_grad[2]:
             dbias = dG2[:, :5 * H].sum(0)
-        return dG, dWh, dbias, None, None, None, None, None
+        return dG, dWh, dbias, None, None, None, None, None, None
 
 
 class AlternatingHighwayLSTM(torch.nn.Module):
@@ -176,7 +209,7 @@ class AlternatingHighwayLSTM(torch.nn.Module):
             # cublasSgemm per step, highway_lstm_kernel.cu:441-452)
             P = tc_ops.matmul_tc(x.view(T * B, insz), wi, self.weight, ("wi", layer)).view(T, B, 6 * H)
             x = _HighwayLayerFunction.apply(P, wh, b, dropout_weights[layer], lengths_dev, layer % 2, save_gates,
-                                            self.weight)
+                                            self.weight, ("wh", layer))
         output = x
         output = pack_padded_sequence(output, lengths, batch_first=False)
         return output, None

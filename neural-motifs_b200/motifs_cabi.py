@@ -69,6 +69,8 @@ SIGNATURES = {
     "mb200_conv_set_halo_mode": (c_int, [c_int]),
     "mb200_decoder_commit": (c_int, [P, P, c_int, c_int, c_float, P, P]),
     "mb200_sgd_momentum_clip_split": (c_int, [P, P, P, P, P, c_longlong, c_float, c_float, c_float, P, c_float, c_float, c_int, c_int, P]),
+    "mb200_highway_lstm_tc_supported": (c_int, [c_int, c_int]),
+    "mb200_highway_lstm_layer_forward_tc": (c_int, [c_int, c_int, c_int, c_int, P, P, P, P, P, P, P, P, P, P, P, P]),
     "mb200_sgemm": (c_int, [c_int, c_int, c_int, c_int, c_int, c_float, P, c_int, P, c_int, c_float, P, c_int, P]),
 }
 

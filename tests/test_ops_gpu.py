@@ -437,3 +437,43 @@ def test_decoder_commit_kernel_identical_to_host_loop(cuda, N, seed):
     b = torch.from_numpy(boxes).to(cuda); p = torch.from_numpy(probs).to(cuda)
     C.check(C.load().mb200_decoder_commit(C.ptr(b), C.ptr(p), N, Cn, 0.3, C.ptr(got), C.cur_stream()), "mb200_decoder_commit")
     assert np.array_equal(got.cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("T,B,In,H,L", [(6, 256, 40, 128, 2), (5, 200, 712, 512, 2), (4, 64, 33, 64, 1), (3, 130, 20, 192, 3)])
+def test_highway_lstm_tensor_core_recurrence(cuda, T, B, In, H, L):
+    """csrc/lstm_tc.cu (per-step [B,H] x [H,5H] on tcgen05, bf16x3, weight slices resident in shared memory; used for
+    B >= 48) against the oracle and against the SIMT kernels on the same inputs: ragged lengths, both directions, training
+    mode (gates saved, backward through the unchanged SIMT backward kernel)."""
+    from torch.nn.utils.rnn import pack_padded_sequence, pad_packed_sequence
+    import lib.lstm.highway_lstm_cuda.alternating_highway_lstm as AH
+    assert AH.use_tensor_core_recurrence(H, B)
+    lengths = sorted([max(1, T - (i * T) // B) for i in range(B)], reverse=True)
+    lengths[0] = T
+    rng = np.random.RandomState(T * 100 + B)
+    m, x, drop = lstm_inputs(rng, T, B, In, H, L, lengths)
+    gout = torch.randn(T, B, H)
+    for b, l in enumerate(lengths):
+        gout[l:, b] = 0
+    mc = m.to(cuda).train()
+
+    def run(tc):
+        AH.TC_RECURRENCE = tc
+        try:
+            mc.zero_grad()
+            xc = x.to(cuda).requires_grad_(True)
+            out_p, _ = mc(pack_padded_sequence(xc, lengths), dropout_weights=drop.to(cuda))
+            out_c, _ = pad_packed_sequence(out_p, total_length=T)
+            (out_c * gout.to(cuda)).sum().backward()
+            return out_c.detach().cpu(), xc.grad.cpu(), mc.weight.grad.detach().cpu().clone(), mc.bias.grad.detach().cpu().clone()
+        finally:
+            AH.TC_RECURRENCE = True
+    o_tc, gx_tc, gw_tc, gb_tc = run(True)
+    o_si, gx_si, gw_si, gb_si = run(False)
+    np.testing.assert_allclose(o_tc.numpy(), o_si.numpy(), rtol=1e-4, atol=3e-5)
+    scale = float(gw_si.abs().max())
+    np.testing.assert_allclose(gx_tc.numpy(), gx_si.numpy(), rtol=1e-3, atol=2e-4)
+    np.testing.assert_allclose(gw_tc.numpy(), gw_si.numpy(), rtol=1e-3, atol=2e-4 * max(1.0, scale))
+    np.testing.assert_allclose(gb_tc.numpy(), gb_si.numpy(), rtol=1e-3, atol=2e-4 * max(1.0, scale))
+    if B * T * H <= 256 * 6 * 128:                       # the oracle (CPU) on the smallest case
+        out_o = oracle_lstm(x, lengths, m.weight.detach().cpu(), m.bias.detach().cpu(), drop, H, L)
+        np.testing.assert_allclose(o_tc.numpy(), out_o.detach().numpy(), rtol=1e-4, atol=3e-5)

@@ -116,9 +116,8 @@ def test_resnet101_shapes_for_the_detector_config():
 
 
 def test_resnet_detector_state_dict_keys_match_between_product_and_oracle(monkeypatch):
-    """Construction only (no CUDA): the product's gated ResNet detector and the oracle's carry the same state dict
+    """Construction only (no CUDA): the product's ResNet detector and the oracle's carry the same state dict
     (the reference's module tree, lib/object_detector.py:84-103), and the oracle one runs on the CPU."""
-    monkeypatch.setenv("MOTIFS_EXPERIMENTAL_RESNET", "1")
     import numpy as np
     import pytest
     from lib.object_detector import ObjectDetector
@@ -128,9 +127,6 @@ def test_resnet_detector_state_dict_keys_match_between_product_and_oracle(monkey
     orc = OM.ObjectDetector(classes, mode='gtbox', use_resnet=True)
     assert set(prod.state_dict().keys()) == set(orc.state_dict().keys())
     orc.load_state_dict(prod.state_dict())
-    monkeypatch.setenv("MOTIFS_EXPERIMENTAL_RESNET", "0")
-    with pytest.raises(NotImplementedError):
-        ObjectDetector(classes, mode='gtbox', use_resnet=True)
     orc.eval()
     x = torch.randn(1, 3, 128, 160)
     gt_boxes = torch.tensor([[10., 12., 90., 100.], [30., 40., 150., 120.]])
