@@ -191,8 +191,9 @@ def run_b200(args):
     # wants exactly one JSON line there. Keep the lines (they are the evidence of the communicator's size) but move
     # everything that is not the JSON line to stderr: fd 1 is pointed at fd 2 for the run, the JSON line is written to
     # the saved original stdout at the end.
-    os.environ.setdefault("NCCL_DEBUG", "INFO")
-    os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+    if "MOTIFS_KEEP_NCCL_DEBUG" not in os.environ:       # (the image presets NCCL_DEBUG=VERSION: only the banner would appear)
+        os.environ["NCCL_DEBUG"] = "INFO"
+        os.environ["NCCL_DEBUG_SUBSYS"] = "INIT"
     sys.stdout.flush()
     real_stdout = os.dup(1)
     os.dup2(2, 1)
@@ -282,7 +283,7 @@ def run_b200(args):
         losses.append(train_step(model, opt, reducer, blob=blobs[i % len(blobs)]))
 
     gc.collect()
-    for i in range(2):
+    for i in range(6):          # the e2e leg allocates the device batch every step: let the allocator settle on that too
         e2e_step(i)
     ms_e2e = timed(e2e_step, args.steps)
     clocks = sampler.stop()

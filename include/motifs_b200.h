@@ -230,6 +230,10 @@ int mb200_gemm_bf16x3_mn(const void* Ahi, const void* Alo, long long lda, const 
 /* tcgen05 GEMM / conv kernel selection: 0 = 1-CTA kernels only, 1 = per-shape choice (default), 2 = the CTA-pair
  * (cta_group::2, 256-row tiles) kernel whenever the shape allows. Returns the previous mode. Tests and A/B runs. */
 int mb200_gemm_set_pair_mode(int mode);
+/* SMs the persistent tcgen05 kernels may occupy (clamped to [16, 148], even). Lowered by the host while a gradient
+ * all-reduce is in flight (NCCL's channel CTAs hold SMs: a full-width persistent grid would run its last CTAs in a second
+ * wave). Returns the previous value. */
+int mb200_set_sm_budget(int n);
 /* 3x3 convolution kernel: 0 = tap-by-tap shifted TMA boxes, 1 = per layer (default), 2 = shared-memory halo staging always. */
 int mb200_conv_set_halo_mode(int mode);
 

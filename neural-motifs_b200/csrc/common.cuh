@@ -34,3 +34,9 @@ void mb200_set_error(const char* what, cudaError_t err);
 static inline int mb200_div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 constexpr int kNumSMs = 148;  // B200
+
+// SMs the persistent tensor-core kernels may occupy (<= kNumSMs, even). While a gradient all-reduce is in flight NCCL's
+// channel CTAs hold SMs for milliseconds; a persistent grid of 148 CTAs with 200 KB of shared memory each then runs its
+// last CTAs in a SECOND wave (they cannot co-reside with NCCL's), i.e. the kernel takes twice as long. The host lowers the
+// budget for launches that may overlap a collective (mb200_set_sm_budget) and restores it afterwards.
+extern int g_mb200_sm_budget;

@@ -272,7 +272,7 @@ int mb200_gemm_bf16x3_mn(const void* Ahi, const void* Alo, long long lda, const 
   }
   const long long tiles = (long long)p.splits * p.m_tiles * p.n_tiles;
   if (tiles > 0x7fffffffLL) return MB200_ERR_UNSUPPORTED;
-  const int grid = (int)min(tiles, (long long)kNumSMs);
+  const int grid = (int)min(tiles, (long long)g_mb200_sm_budget);
   if (bn == 256) gemm_bf16x3_mn_kernel<256><<<grid, kThreads, Cfg<256>::SMEM_BYTES, stream>>>(ta, tal, tb, tbl, p);
   else gemm_bf16x3_mn_kernel<128><<<grid, kThreads, Cfg<128>::SMEM_BYTES, stream>>>(ta, tal, tb, tbl, p);
   MB200_CHECK_LAUNCH("gemm_bf16x3_mn_kernel");

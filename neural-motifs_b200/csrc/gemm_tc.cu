@@ -815,7 +815,7 @@ int launch(const CUtensorMap& ahi, const CUtensorMap& alo, const CUtensorMap& bh
   if (pair_bn) {
     const long long tiles = (long long)p.splits * ((p.m_tiles + 1) / 2) * p.n_tiles;
     if (tiles > 0x7fffffffLL) return MB200_ERR_UNSUPPORTED;
-    const int grid = 2 * (int)min(tiles, (long long)(kNumSMs / 2));         // persistent: one CTA pair per TPC
+    const int grid = 2 * (int)min(tiles, (long long)(g_mb200_sm_budget / 2));   // persistent: one CTA pair per TPC
     if (pair_bn == 256)
       gemm_bf16x3_2cta_kernel<256><<<grid, kGemmThreads, Cfg2<256>::SMEM_BYTES, stream>>>(ahi, alo, bhi, blo, p, num_images);
     else if (pair_bn == 128)
@@ -827,7 +827,7 @@ int launch(const CUtensorMap& ahi, const CUtensorMap& alo, const CUtensorMap& bh
   }
   const long long tiles = (long long)p.splits * p.m_tiles * p.n_tiles;
   if (tiles > 0x7fffffffLL) return MB200_ERR_UNSUPPORTED;
-  const int grid = (int)min(tiles, (long long)kNumSMs);      // persistent: one CTA per SM
+  const int grid = (int)min(tiles, (long long)g_mb200_sm_budget);      // persistent: one CTA per SM
   if (bn == 256) gemm_bf16x3_kernel<256><<<grid, kGemmThreads, Cfg<256>::SMEM_BYTES, stream>>>(ahi, alo, bhi, blo, p);
   else gemm_bf16x3_kernel<128><<<grid, kGemmThreads, Cfg<128>::SMEM_BYTES, stream>>>(ahi, alo, bhi, blo, p);
   MB200_CHECK_LAUNCH("gemm_bf16x3_kernel");
@@ -932,7 +932,7 @@ int mb200_conv3x3_bf16x3(const void* xhi, const void* xlo, const void* whi, cons
     p.m_tiles = (int)sp; p.n_tiles = mb200_div_up(Cout, bn);
     const long long tiles = ((sp + 1) / 2) * p.n_tiles;
     if (tiles > 0x7fffffffLL) return MB200_ERR_UNSUPPORTED;
-    const int grid = 2 * (int)min(tiles, (long long)(kNumSMs / 2));
+    const int grid = 2 * (int)min(tiles, (long long)(g_mb200_sm_budget / 2));
     if (bn == 256) conv3x3_halo_2cta_kernel<256><<<grid, kGemmThreads, CfgH<256>::SMEM_BYTES, stream>>>(ta, tal, tb, tbl, p, B);
     else if (bn == 128) conv3x3_halo_2cta_kernel<128><<<grid, kGemmThreads, CfgH<128>::SMEM_BYTES, stream>>>(ta, tal, tb, tbl, p, B);
     else conv3x3_halo_2cta_kernel<64><<<grid, kGemmThreads, CfgH<64>::SMEM_BYTES, stream>>>(ta, tal, tb, tbl, p, B);

@@ -3,6 +3,7 @@
 #include <string.h>
 
 static thread_local char g_err[512] = "";
+int g_mb200_sm_budget = kNumSMs;
 
 void mb200_set_error(const char* what, cudaError_t err) {
   snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(err));
@@ -14,6 +15,16 @@ const char* mb200_last_error() { return g_err; }
 
 // ABI version of include/motifs_b200.h this library implements.
 int mb200_abi_version() { return 1; }
+
+// SM budget of the persistent tcgen05 kernels (see common.cuh); n is clamped to [16, 148] and rounded down to even.
+// Returns the previous budget.
+int mb200_set_sm_budget(int n) {
+  const int old = g_mb200_sm_budget;
+  if (n > kNumSMs) n = kNumSMs;
+  if (n < 16) n = 16;
+  g_mb200_sm_budget = n & ~1;
+  return old;
+}
 
 // Compiled architecture (100 => sm_100a). Lets the host fail loudly on a mismatched device.
 int mb200_compiled_arch() { return 100; }

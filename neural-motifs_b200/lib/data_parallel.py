@@ -19,6 +19,8 @@ def init_from_env(backend=None):
             backend = "nccl" if torch.cuda.is_available() else "gloo"
         if backend == "nccl":
             torch.cuda.set_device(local)
+            # NCCL's channel count is left at its default (32 over NVSwitch): the 1.1 GB gradient all-reduce is bandwidth
+            # bound and capping it at 8 / 4 channels cost 2.3 / 8.9 ms per step at N=2 (profiles/r02_nccl_channels.json)
         dist.init_process_group(backend=backend, rank=rank, world_size=world)
     return rank, world, local
 

@@ -66,6 +66,7 @@ SIGNATURES = {
     "mb200_sgd_momentum_clip_scaled": (c_int, [P, P, P, c_longlong, c_float, c_float, c_float, P, c_float, c_float, c_int, c_int, P]),
     "mb200_anchor_targets": (c_int, [P, c_int, P, c_int, c_double, c_double, P, P, P, P, P]),
     "mb200_gemm_set_pair_mode": (c_int, [c_int]),
+    "mb200_set_sm_budget": (c_int, [c_int]),
     "mb200_conv_set_halo_mode": (c_int, [c_int]),
     "mb200_decoder_commit": (c_int, [P, P, c_int, c_int, c_float, P, P]),
     "mb200_sgd_momentum_clip_split": (c_int, [P, P, P, P, P, c_longlong, c_float, c_float, c_float, P, c_float, c_float, c_int, c_int, P]),

@@ -69,12 +69,42 @@ def test_roi_align_nhwc_matches_nchw(cuda):
     assert torch.equal(a.permute(0, 2, 3, 1).reshape(77, 49, 512), b)
 
 
+@pytest.mark.parametrize("C,ph,pw", [(512, 7, 7), (136, 7, 7), (256, 3, 5), (64, 7, 14), (128, 1, 1), (512, 8, 8)])
+def test_roi_align_nhwc_separable_edge_cases(cuda, C, ph, pw):
+    """The column-separable NHWC kernel (crop height <= 7) is bit-equal to the NCHW kernel (itself bit-equal to the
+    reference's) on whole-image, partly / fully outside, degenerate, DESCENDING and bad-batch rois; 8x8 takes the per-bin
+    kernel."""
+    from lib.fpn.roi_align.functions.roi_align import RoIAlignFunction, roi_align_nhwc
+    rng = np.random.RandomState(C + ph)
+    feat = torch.from_numpy(rng.randn(3, C, 37, 37).astype(np.float32)).to(cuda)
+    r = rois_for(rng, 64, 3)
+    r[0, 1:] = [0, 0, 591, 591]
+    r[1, 1:] = [-40, -40, 100, 100]
+    r[2, 1:] = [300, 300, 300, 300]
+    r[3, 1:] = [400, 380, 200, 120]          # x2 < x1, y2 < y1: sample rows run downwards
+    r[4, 1:] = [-500, -500, -300, -300]      # entirely outside
+    r[5, 1:] = [100, -90, 180, 700]          # rows outside at both ends, >1 px apart in between
+    r[6, 0] = 9                              # bad batch index
+    r[7, 1:] = [64, 64, 160, 160]            # samples on exact pixel centres (lo == hi)
+    r[8, 1:] = [10, 500, 300, 591]
+    rois = torch.from_numpy(r).to(cuda)
+    a = RoIAlignFunction(ph, pw, 1 / 16)(feat, rois)
+    b = roi_align_nhwc(feat.permute(0, 2, 3, 1).contiguous(), rois, ph, pw, 1 / 16)
+    assert torch.equal(a.permute(0, 2, 3, 1).reshape(64, ph * pw, C), b)
+
+
 def test_roi_align_backward_vs_oracle(cuda):
     from lib.fpn.roi_align.functions.roi_align import RoIAlignFunction
     rng = np.random.RandomState(9)
     B, C, N = 2, 16, 25
     feat = torch.from_numpy(rng.randn(B, C, 37, 37).astype(np.float32)).to(cuda).requires_grad_(True)
     rois = rois_for(rng, N, B)
+    rois[0, 1:] = [0, 0, 591, 591]            # window larger than the windowed backward path takes -> per-bin atomics
+    rois[1, 1:] = [-40, -40, 100, 100]        # partly outside
+    rois[2, 1:] = [300, 300, 300, 300]        # degenerate: all 49 bins on one point
+    rois[3, 1:] = [400, 380, 200, 120]        # descending
+    rois[4, 1:] = [64, 64, 160, 160]          # samples on pixel centres (lo == hi)
+    rois[5, 1:] = [100, -90, 180, 700]        # rows outside at both ends
     g = rng.randn(N, C, 7, 7).astype(np.float32)
     out = RoIAlignFunction(7, 7, 1 / 16)(feat, torch.from_numpy(rois).to(cuda))
     out.backward(torch.from_numpy(g).to(cuda))
