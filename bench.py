@@ -321,6 +321,8 @@ def run_b200(args):
         "config": {"workload": "MotifNet SGCls train_rels.py step, VGG16 backbone, batch 6x592x592 per GPU, "
                                "20 GT boxes + 15 GT rels per image (1536 rel triples), fwd+bwd+clip+SGD",
                    "global_batch": BATCH_PER_GPU * world, "parallelism": "dp%d" % world,
+                   "dp_comm": {"nvls": "sharded update over NVSwitch multicast (own kernels: multimem.ld_reduce / multimem.st)",
+                               "nccl": "NCCL all-reduce of the flat gradient", "ce": "sharded update, gradient shards and updated parameters moved by copy engines over NVLink (peer-mapped symmetric memory)", "none": "single GPU"}[opt.comm],
                    "warmup_steps_run": W,
                    "arithmetic": "fp32 semantics: tcgen05 bf16x3 split-operand GEMM/conv, fp32 accumulate",
                    "l2": "per-step working set (1.7 GB params + activations) >> 126 MB L2; 4 rotating batches"},

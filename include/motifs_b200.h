@@ -234,6 +234,8 @@ int mb200_gemm_set_pair_mode(int mode);
  * all-reduce is in flight (NCCL's channel CTAs hold SMs: a full-width persistent grid would run its last CTAs in a second
  * wave). Returns the previous value. */
 int mb200_set_sm_budget(int n);
+/* cudaMemsetAsync(ptr, 0, bytes, stream): zero-fill without occupying an SM. */
+int mb200_zero_async(void* ptr, long long bytes, cudaStream_t stream);
 /* 3x3 convolution kernel: 0 = tap-by-tap shifted TMA boxes, 1 = per layer (default), 2 = shared-memory halo staging always. */
 int mb200_conv_set_halo_mode(int mode);
 
@@ -268,6 +270,30 @@ int mb200_sgd_momentum_clip_scaled(float* params, float* grads, float* momentum_
 int mb200_sgd_momentum_clip_split(float* params, float* grads, float* momentum_buf, void* hi, void* lo, long long n, float lr,
                                   float momentum, float weight_decay, const float* total_norm_dev, float max_norm,
                                   float grad_scale, int first_step, int zero_grad, cudaStream_t stream);
+
+/* ---- Data-parallel sharded update over NVSwitch multicast (lib/fused_optim.py, comm="nvls"; replaces the reference's
+ * replicate / parallel_apply / Gather of lib/rel_model.py:549-560 together with the gradient exchange). `*_mc` arguments are
+ * MULTICAST virtual addresses of symmetric buffers (one physical copy per rank, same offset everywhere), obtained by the host
+ * from torch's symmetric-memory rendezvous; everything else is an ordinary local device pointer.
+ *   pass 1  mb200_dp_reduce_shard_sumsq: out[i] = SUM over ranks of the gradient at x_mc[i] (multimem.ld_reduce: the sum is
+ *           formed inside the switch), *acc += sum of out[i]^2                                   -> reduce-scatter + norm
+ *           mb200_dp_bcast_slot: *v -> slots[idx] on every rank                                  -> the ranks' partial norms
+ *   pass 2  mb200_sgd_momentum_clip_mc: the fused clip + SGD update of this rank's shard, the new parameters (and their bf16
+ *           operand pairs when hi_mc / lo_mc are non-null) stored with multimem.st into EVERY rank's copy   -> all-gather
+ * n % 4 == 0, 16-byte aligned (8 for hi / lo). The caller orders the passes with cross-rank barriers.
+ * mb200_optim_set_background(1): sumsq / sgd / the two passes launch as ONE 128-thread CTA per SM (<= 80 registers), which
+ * fits beside a resident tcgen05 GEMM CTA — for updates deferred underneath the next step's backbone. */
+/* comm="ce": the gradient shards travel by COPY ENGINE over NVLink (peer-mapped symmetric memory, no SM involved);
+ * the only kernels are local and shard-sized: g[i] += sum of the nslots staged copies (stage + k * stride), *acc += |g|^2,
+ * then the ordinary mb200_sgd_momentum_clip_split on the shard; the updated shard is copied back out by the copy engines. */
+int mb200_dp_reduce_staged_sumsq(float* g, const float* stage, long long stride, int nslots, long long n, double* acc,
+                                 cudaStream_t stream);
+int mb200_optim_set_background(int on);
+int mb200_dp_reduce_shard_sumsq(const float* x_mc, float* out, long long n, double* acc, cudaStream_t stream);
+int mb200_dp_bcast_slot(const double* v, double* slots_mc, int idx, cudaStream_t stream);
+int mb200_sgd_momentum_clip_mc(float* params, float* grads, float* momentum_buf, float* p_mc, void* hi_mc, void* lo_mc,
+                               long long n, float lr, float momentum, float weight_decay, const float* total_norm_dev,
+                               float max_norm, float grad_scale, int first_step, int zero_grad, cudaStream_t stream);
 
 #ifdef __cplusplus
 }

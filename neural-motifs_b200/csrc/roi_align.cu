@@ -17,8 +17,6 @@
 //     contiguous 16-byte vector stores (the output of a chunk is one contiguous run);
 //   * NHWC: lanes are channel quads, loads and stores are 16-byte vectors straight from L2;
 //   * windows larger than 256 px (bins >= 1 px apart, no re-use to exploit) gather from global.
-#include <cstdlib>
-#include <type_traits>
 #include "common.cuh"
 
 namespace {
@@ -27,8 +25,6 @@ constexpr int kMaxCrop = 32;     // fast kernels: crop_h, crop_w <= 32 and crop_
 constexpr int kMaxBins = 256;
 constexpr int kThreads = 256;
 constexpr int kChunk   = 32;     // channels per CTA (backward kernel)
-constexpr int kBwdMaxCrop = 8;   // backward, windowed path: crops up to 8x8 ...
-constexpr int kBwdMaxWin = 16;   // ... whose window on the feature map is at most 16x16 px
 
 struct BinTab {
   int   o00[kMaxBins], o01[kMaxBins], o10[kMaxBins], o11[kMaxBins];
@@ -348,155 +344,12 @@ roi_align_fwd_nhwc_kernel(const float* __restrict__ feat, const float* __restric
   }
 }
 
-// ---------------------------------------------------------------- forward, NHWC, separable ("column") variant
-// ncu on the per-bin kernel above (profiles/r02_ncu_roi_nhwc_details.csv): 12.9 M L1 load sectors (411 MB, 4 corner
-// loads per output) against 103 MB of output, l1tex data-pipe wavefronts 62 % of peak, HBM 3 % — the gather through L1
-// is the bound, not memory. The bilinear sample is separable in exactly the order the reference evaluates it:
-//   top = fma(wx, tr - tl, tl), bottom = fma(wx, br - bl, bl), out = fma(wy, bottom - top, top)
-// so `top` / `bottom` are functions of (feature row, bin column) only. A warp owns one bin COLUMN x for 128 channels:
-// it loads the two pixels (x_lo, x_hi) of every DISTINCT feature row the roi's PH bins touch (<= 2 PH rows; 5-8 for
-// the usual box whose bins are less than a pixel apart), forms the horizontal lerps once, and emits the PH outputs of
-// the column from adjacent pairs. Loads per (column, lane): 2 x rows instead of 4 x PH; results are bit-identical.
-constexpr int kColRows = 14;          // distinct feature rows per roi (2 x PH, PH <= 7)
-constexpr int kColMaxPH = 7;
-constexpr int kColWarps = 7;
-constexpr int kColThreads = kColWarps * 32;
-constexpr int kColChunk = 256;        // channels per CTA
-
-template <bool CHW>
-__global__ void __launch_bounds__(kColThreads, 2)
-roi_align_fwd_nhwc_cols_kernel(const float* __restrict__ feat, const float* __restrict__ boxes,
-                               int num_boxes, int batch, int H, int W, int PH, int PW, int C,
-                               float extrap, float* __restrict__ out) {
-  extern __shared__ __align__(16) float s_ctile[];         // CHW only: [kColChunk][bins]
-  __shared__ AxisTab ty, tx;
-  __shared__ RoiHead hd;
-  __shared__ int s_rowoff[kColRows];
-  __shared__ int s_ia[kColMaxPH + 1], s_ib[kColMaxPH + 1];
-  __shared__ int s_nrows, s_ordered;
-  const int n = blockIdx.x;
-  const int c0 = blockIdx.y * kColChunk;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int bins = PH * PW;
-  roi_preamble(boxes, n, batch, H, W, PH, PW, ty, tx, hd);
-  if (tid == 0) {
-    // distinct rows in order of first use; ascending box coordinates give ia non-decreasing and ib in {ia, ia + 1}
-    int rows[kColRows];
-    int nr = 0, ordered = 1, prev = -1;
-    for (int y = 0; y < PH; ++y) {
-      if (!ty.ok[y]) { s_ia[y] = -1; s_ib[y] = -1; continue; }
-      const int lo = ty.lo[y], hi = ty.hi[y];
-      int ia = -1, ib = -1;
-      for (int k = 0; k < nr; ++k) if (rows[k] == lo) ia = k;
-      if (ia < 0) { rows[nr] = lo; ia = nr++; }
-      for (int k = 0; k < nr; ++k) if (rows[k] == hi) ib = k;
-      if (ib < 0) { rows[nr] = hi; ib = nr++; }
-      if (ia < prev || (ib != ia && ib != ia + 1)) ordered = 0;
-      prev = ia;
-      s_ia[y] = ia; s_ib[y] = ib;
-    }
-    for (int k = 0; k < nr; ++k) s_rowoff[k] = rows[k] * W * C;
-    s_nrows = nr; s_ordered = ordered;
-  }
-  __syncthreads();
-  const float* img0 = feat + (size_t)(hd.bad_batch ? 0 : hd.b_in) * H * W * C;
-  float* o0 = out + (size_t)n * bins * C;
-  const int nrows = s_nrows;
-  const int nq = kColChunk / 128;
-  for (int task = warp; task < PW * nq; task += kColWarps) {
-    const int x = task % PW, q = task / PW;
-    const int c = c0 + q * 128 + 4 * lane;
-    if (c >= C) continue;
-    // bin-major: bin (y, x) of channels c..c+3 is one float4 at o0[(y * PW + x) * C + c]; CHW: four words of the
-    // [channel][bin] tile, written out as one contiguous run after the loop
-    float* oc = CHW ? (s_ctile + (size_t)(q * 128 + 4 * lane) * bins + x) : (o0 + (size_t)x * C + c);
-    const size_t ystep = CHW ? (size_t)PW : (size_t)PW * C;
-    auto emit = [&](int y, const float4& v) {
-      float* t = oc + y * ystep;
-      if (CHW) { t[0] = v.x; t[bins] = v.y; t[2 * bins] = v.z; t[3 * bins] = v.w; }
-      else *(float4*)t = v;
-    };
-    if (hd.bad_batch || !tx.ok[x]) {
-      const float e = hd.bad_batch ? 0.f : extrap;
-      for (int y = 0; y < PH; ++y) emit(y, make_float4(e, e, e, e));
-      continue;
-    }
-    const float* img = img0 + c;
-    const int xl = tx.lo[x] * C, xr = tx.hi[x] * C;
-    const float wx = tx.lerp[x];
-    if (!s_ordered) {                                   // descending / degenerate boxes: the plain four-corner form
-      for (int y = 0; y < PH; ++y) {
-        float4 v = make_float4(extrap, extrap, extrap, extrap);
-        if (ty.ok[y]) {
-          const float* r0 = img + (size_t)ty.lo[y] * W * C;
-          const float* r1 = img + (size_t)ty.hi[y] * W * C;
-          const float4 tl = __ldg((const float4*)(r0 + xl)), tr = __ldg((const float4*)(r0 + xr));
-          const float4 bl = __ldg((const float4*)(r1 + xl)), br = __ldg((const float4*)(r1 + xr));
-          const float wy = ty.lerp[y];
-          v.x = bilerp(tl.x, tr.x, bl.x, br.x, wx, wy); v.y = bilerp(tl.y, tr.y, bl.y, br.y, wx, wy);
-          v.z = bilerp(tl.z, tr.z, bl.z, br.z, wx, wy); v.w = bilerp(tl.w, tr.w, bl.w, br.w, wx, wy);
-        }
-        emit(y, v);
-      }
-      continue;
-    }
-    // horizontal lerps of the distinct rows live in registers: the row loop must be fully unrolled with ALL loads issued
-    // before the first use (a runtime row count inside one unrolled loop serialised them: 98 us instead of 35), so the
-    // body is instantiated for 4/6/8/10/12/14 rows and the surplus slots re-read the last row (an L1 hit)
-    auto run = [&](auto nr_tag) {
-      constexpr int NR = decltype(nr_tag)::value;
-      float4 lft[NR], rgt[NR];
-#pragma unroll
-      for (int k = 0; k < NR; ++k) {
-        const float* p = img + s_rowoff[k < nrows ? k : nrows - 1];
-        lft[k] = __ldg((const float4*)(p + xl)); rgt[k] = __ldg((const float4*)(p + xr));
-      }
-      float4 hrow[NR];
-#pragma unroll
-      for (int k = 0; k < NR; ++k) {
-        hrow[k].x = __fmaf_rn(wx, rgt[k].x - lft[k].x, lft[k].x); hrow[k].y = __fmaf_rn(wx, rgt[k].y - lft[k].y, lft[k].y);
-        hrow[k].z = __fmaf_rn(wx, rgt[k].z - lft[k].z, lft[k].z); hrow[k].w = __fmaf_rn(wx, rgt[k].w - lft[k].w, lft[k].w);
-      }
-      int y = 0;
-#pragma unroll
-      for (int k = 0; k < NR; ++k) {
-        while (y < PH) {
-          const int ia = s_ia[y];
-          if (ia > k) break;
-          float4 v = make_float4(extrap, extrap, extrap, extrap);
-          if (ia == k) {
-            const float4 a = hrow[k];
-            const float4 b = (k + 1 < NR && s_ib[y] != k) ? hrow[k + 1 < NR ? k + 1 : k] : a;
-            const float wy = ty.lerp[y];
-            v.x = __fmaf_rn(wy, b.x - a.x, a.x); v.y = __fmaf_rn(wy, b.y - a.y, a.y);
-            v.z = __fmaf_rn(wy, b.z - a.z, a.z); v.w = __fmaf_rn(wy, b.w - a.w, a.w);
-          }
-          emit(y, v);
-          ++y;
-        }
-      }
-      for (; y < PH; ++y) emit(y, make_float4(extrap, extrap, extrap, extrap));
-    };
-    if (nrows == 0) { for (int y = 0; y < PH; ++y) emit(y, make_float4(extrap, extrap, extrap, extrap)); }
-    else if (nrows <= 4) run(std::integral_constant<int, 4>());
-    else if (nrows <= 6) run(std::integral_constant<int, 6>());
-    else if (nrows <= 8) run(std::integral_constant<int, 8>());
-    else if (nrows <= 10) run(std::integral_constant<int, 10>());
-    else if (nrows <= 12) run(std::integral_constant<int, 12>());
-    else run(std::integral_constant<int, kColRows>());
-  }
-  if (CHW) {   // the chunk's [nc][bins] block is one contiguous run in global memory
-    __syncthreads();
-    const int nc = min(kColChunk, C - c0);
-    float* dst = out + ((size_t)n * C + c0) * bins;
-    const int total = nc * bins;
-    if ((total % 4 == 0) && ((((uintptr_t)dst) & 15) == 0)) {
-      for (int i = tid; i < total / 4; i += kColThreads) ((float4*)dst)[i] = ((const float4*)s_ctile)[i];
-    } else {
-      for (int i = tid; i < total; i += kColThreads) dst[i] = s_ctile[i];
-    }
-  }
-}
+// Tried and removed (round 2, profiles/r02_microbench_roi_{perbin,cols}.json): a SEPARABLE variant — a warp owns one bin
+// column, loads the two pixels of every distinct feature row once (2 x rows instead of 4 x PH loads) and forms the
+// horizontal lerps once, bit-identical results. ncu had shown the per-bin kernel bound by L1 load wavefronts (411 MB of
+// corner loads for 103 MB of output), so 35-60 % fewer loads looked like the lever; measured it was 2.3x SLOWER (78.8 vs
+// 34.8 us at N=1024): 80-128 registers for the row cache leave 14 warps per SM, and the dependent emission loop after the
+// load batch exposes latency the per-bin kernel hides with 24 warps x 16 independent loads.
 
 // scalar NHWC fallback for channel counts that are not a multiple of 4
 __global__ void __launch_bounds__(kThreads)
@@ -543,46 +396,10 @@ roi_align_bwd_nchw_kernel(const float* __restrict__ grads, const float* __restri
   const int bins = PH * PW;
   build_tables(boxes, n, batch, H, W, PH, PW, ty, tx, info);
   if (!info.any_ok) return;
-  if (PH <= kBwdMaxCrop && PW <= kBwdMaxCrop && info.wh <= kBwdMaxWin && info.ww <= kBwdMaxWin) {
-    // Small window (boxes up to ~220 px at stride 16): the transpose of the separable forward, evaluated WITHOUT
-    // atomics in shared memory — first along x (bins -> window columns), then along y (-> window rows) — and one
-    // global atomic per window pixel instead of four per bin: wh*ww (typ. 30-100) instead of 4*PH*PW = 196 per channel.
-    // The reference kernel and the direct path below are bound by L2 atomic throughput (N=8192: 822 M atomics).
-    __shared__ float s_g[kChunk][kBwdMaxCrop * kBwdMaxCrop];
-    __shared__ float s_t[kChunk][kBwdMaxCrop][kBwdMaxWin];
-    const float* g = grads + ((size_t)n * C + c0) * bins;
-    for (int i = tid; i < nc * bins; i += kThreads) s_g[i / bins][i % bins] = g[i];
-    __syncthreads();
-    const int ww = info.ww, wh = info.wh;
-    for (int i = tid; i < nc * PH * ww; i += kThreads) {
-      const int sx = i % ww, y = (i / ww) % PH, c = i / (ww * PH);
-      const int col = info.x_lo + sx;
-      float acc = 0.f;
-      if (ty.ok[y])
-        for (int x = 0; x < PW; ++x) {
-          if (!tx.ok[x]) continue;
-          const float gv = s_g[c][y * PW + x], wx = tx.lerp[x];
-          if (tx.lo[x] == col) acc += (1 - wx) * gv;
-          if (tx.hi[x] == col) acc += wx * gv;
-        }
-      s_t[c][y][sx] = acc;
-    }
-    __syncthreads();
-    float* plane0 = gimg + ((size_t)info.b_in * C + c0) * H * W;
-    for (int i = tid; i < nc * wh * ww; i += kThreads) {
-      const int sx = i % ww, r = (i / ww) % wh, c = i / (ww * wh);
-      const int row = info.y_lo + r;
-      float acc = 0.f;
-      for (int y = 0; y < PH; ++y) {
-        if (!ty.ok[y]) continue;
-        const float t = s_t[c][y][sx], wy = ty.lerp[y];
-        if (ty.lo[y] == row) acc += (1 - wy) * t;
-        if (ty.hi[y] == row) acc += wy * t;
-      }
-      if (acc != 0.f) atomicAdd(plane0 + (size_t)c * H * W + row * W + info.x_lo + sx, acc);
-    }
-    return;
-  }
+  // Tried and removed (round 2): accumulating the roi's window in shared memory first (separable transpose, no shared
+  // atomics) and issuing one global atomic per window pixel instead of four per bin — fewer atomics (30-100 vs 196 per
+  // channel) but twice as slow (587 vs 285 us at N=1024, 4.5 vs 2.9 ms at N=8192): the two extra block-wide phases and
+  // their index arithmetic cost more than the L2 atomics they save.
   for (int b = tid; b < bins; b += kThreads) {
     const int y = b / PW, x = b - y * PW;
     tb.ok[b] = ty.ok[y] & tx.ok[x];
@@ -736,25 +553,7 @@ static int roi_align_nhwc_launch(bool chw, const float* image_nhwc, const float*
       attr_set = true;
     }
     if (chw && (size_t)kChunkNHWC * bins * sizeof(float) > max_tile) return MB200_ERR_UNSUPPORTED;
-    static const int cols_mode = [] { const char* e = getenv("MOTIFS_ROI_NHWC_COLS"); return e ? atoi(e) : 1; }();
-    if (cols_mode && crop_height <= kColMaxPH) {
-      dim3 cgrid(num_boxes, mb200_div_up(depth, kColChunk));
-      const size_t tile = (size_t)kColChunk * bins * sizeof(float);          // <= 256 * 7 * 32 * 4 = 229 KB; 7x7: 50 KB
-      static bool cattr_set = false;
-      if (!cattr_set) {
-        MB200_CHECK(cudaFuncSetAttribute(roi_align_fwd_nhwc_cols_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_tile));
-        cattr_set = true;
-      }
-      if (chw && tile > max_tile) return MB200_ERR_UNSUPPORTED;
-      if (chw)
-        roi_align_fwd_nhwc_cols_kernel<true><<<cgrid, kColThreads, tile, stream>>>(
-            image_nhwc, boxes_ptr, num_boxes, batch, image_height, image_width, crop_height, crop_width, depth,
-            extrapolation_value, crops);
-      else
-        roi_align_fwd_nhwc_cols_kernel<false><<<cgrid, kColThreads, 0, stream>>>(
-            image_nhwc, boxes_ptr, num_boxes, batch, image_height, image_width, crop_height, crop_width, depth,
-            extrapolation_value, crops);
-    } else if (chw)
+    if (chw)
       roi_align_fwd_nhwc_kernel<true><<<grid, kThreads, win + (size_t)kChunkNHWC * bins * sizeof(float), stream>>>(
           image_nhwc, boxes_ptr, num_boxes, batch, image_height, image_width, crop_height, crop_width, depth,
           extrapolation_value, crops);

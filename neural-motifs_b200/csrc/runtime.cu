@@ -26,6 +26,14 @@ int mb200_set_sm_budget(int n) {
   return old;
 }
 
+// cudaMemsetAsync(ptr, 0, bytes): zero-fill by the memset engine, no SM involved (a fill KERNEL queued beside the
+// persistent tcgen05 GEMMs would hold up their CTAs; lib/fused_optim.py zeroes gradient shards with this).
+int mb200_zero_async(void* ptr, long long bytes, cudaStream_t stream) {
+  if (bytes <= 0) return MB200_OK;
+  MB200_CHECK(cudaMemsetAsync(ptr, 0, (size_t)bytes, stream));
+  return MB200_OK;
+}
+
 // Compiled architecture (100 => sm_100a). Lets the host fail loudly on a mismatched device.
 int mb200_compiled_arch() { return 100; }
 

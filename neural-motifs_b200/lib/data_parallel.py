@@ -89,7 +89,14 @@ def count_weighted_loss(sums_and_counts):
     if world == 1:
         return sum(s / max(int(n), 1) for s, n in sums_and_counts)
     dev = sums_and_counts[0][0].device
-    tot = torch.tensor([float(n) for _, n in sums_and_counts], device=dev, dtype=torch.float32)
+    # pinned + non_blocking: a pageable `torch.tensor(..., device=dev)` copy is stream-ordered AND host-synchronous, i.e. the
+    # host would sit here until the whole forward has drained and only then start queueing the backward
+    if dev.type == "cuda":
+        import numpy as np
+        from lib.pytorch_misc import to_device_async
+        tot = to_device_async(np.array([float(n) for _, n in sums_and_counts], np.float32), dev)
+    else:
+        tot = torch.tensor([float(n) for _, n in sums_and_counts], device=dev, dtype=torch.float32)
     dist.all_reduce(tot, op=dist.ReduceOp.SUM)
     tot = tot.clamp_min(1.0)
     return sum(s * (world / tot[k]) for k, (s, _) in enumerate(sums_and_counts))

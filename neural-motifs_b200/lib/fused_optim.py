@@ -25,7 +25,23 @@ backward after a chunk has gone out raises (it would add local gradients to an a
 `defer_step=True` (opt-in): `step()` enqueues [wait for the all-reduce, norm, fused update] on a side stream and
 returns at once; the next forward's frozen backbone (9 of 21 ms) runs underneath it and `wait_pending_updates()`
 — called by RelModel / ObjectDetector.forward before the first trainable parameter is read — joins the two
-streams. The gradient all-reduce is then off the critical path entirely at any world size."""
+streams. The gradient all-reduce is then off the critical path entirely at any world size.
+
+Data parallel over NVSwitch (`comm="nvls"`, the default on CUDA when torch's symmetric-memory rendezvous offers multicast):
+gradients, parameters and their bf16 operand pairs live in ONE symmetric allocation per optimizer; each rank owns a
+contiguous shard of every flat buffer and the step is three of our own kernels (csrc/optim.cu) between device-side barriers:
+  barrier A  every rank's backward has finished
+  pass 1     `multimem.ld_reduce.add` of the own shard: the switch returns the sum over all ranks -> local gradient shard,
+             and its squared norm (reduce-scatter + norm, no staging copy); the W partial norms are multicast to all ranks
+  barrier B
+  pass 2     fused clip + SGD on the own shard; the new parameters and operand pairs leave through `multimem.st`, which
+             lands them in EVERY rank's copy (the all-gather is the store)
+  barrier C
+No NCCL kernel takes part: NCCL's 32 channel CTAs cannot share an SM with a 200 KB / 54 K-register tcgen05 GEMM CTA, so an
+all-reduce underneath the backbone pushed the persistent GEMMs into a second wave (+1.4 ms per step at 2 GPUs, profiles/
+r02_nccl_channels.json, r02_trace_gaps_n2.log). The passes launch in the BACKGROUND shape (one 128-thread CTA per SM) that
+does fit beside a GEMM CTA. Momentum exists for the own shard only. `comm="nccl"` keeps the chunked all-reduce (the CPU /
+gloo tests, GPUs without multicast)."""
 import torch
 import torch.distributed as dist
 
@@ -45,8 +61,50 @@ def wait_pending_updates():
         opt._reserve_sms(False)          # kernels queued from here on run after the collectives: full width again
 
 
+def flat_size(params):
+    return sum((p.numel() + 3) // 4 * 4 for p in params)
+
+
+class SymmArena(object):
+    """One symmetric (peer-mapped + multicast-mapped) allocation, carved into typed flat buffers. torch's symmetric
+    memory does the plumbing: cuMem allocation, handle exchange, multicast binding, device-side barrier."""
+
+    def __init__(self, nbytes, device):
+        import torch.distributed._symmetric_memory as symm
+        self.buf = symm.empty(int(nbytes), dtype=torch.uint8, device=device)
+        self.hdl = symm.rendezvous(self.buf, dist.group.WORLD)
+        self.buf.zero_()
+        self.base = self.buf.data_ptr()
+        self.mc_base = int(self.hdl.multicast_ptr) if getattr(self.hdl, "has_multicast_support", False) else 0
+        rank, world = dist.get_rank(), dist.get_world_size()
+        # the other ranks' arenas, mapped into this process (same layout: a view here has the same offset there)
+        self.peers = {q: self.hdl.get_buffer(q, (int(nbytes),), torch.uint8) for q in range(world) if q != rank}
+        self.used = 0
+
+    def peer_view(self, q, t):
+        """The tensor occupying, in rank q's arena, the bytes `t` occupies in this one."""
+        off = t.data_ptr() - self.base
+        return self.peers[q][off:off + t.numel() * t.element_size()].view(t.dtype)
+
+    def take(self, n, dtype):
+        nbytes = n * torch.empty((), dtype=dtype).element_size()
+        t = self.buf[self.used:self.used + nbytes].view(dtype)
+        self.used += (nbytes + 255) // 256 * 256
+        return t
+
+    def mc(self, t):
+        """Multicast address of (the start of) a view of the arena."""
+        import ctypes
+        if not self.mc_base:
+            raise RuntimeError("symmetric memory without multicast support")
+        return ctypes.c_void_p(self.mc_base + (t.data_ptr() - self.base))
+
+    def barrier(self):
+        self.hdl.barrier(channel=0)
+
+
 class FlatGroup(object):
-    def __init__(self, params, chunk_bytes=128 << 20):
+    def __init__(self, params, chunk_bytes=128 << 20, arena=None):
         self.params = params
         dev = params[0].device
         offs, n = [], 0
@@ -55,11 +113,18 @@ class FlatGroup(object):
             n += (p.numel() + 3) // 4 * 4            # keep every view 16-byte aligned
         self.n = n
         self.offs = offs
-        self.flat_p = torch.zeros(n, device=dev, dtype=torch.float32)
-        self.flat_g = torch.zeros(n, device=dev, dtype=torch.float32)
+        if arena is None:
+            self.flat_p = torch.zeros(n, device=dev, dtype=torch.float32)
+            self.flat_g = torch.zeros(n, device=dev, dtype=torch.float32)
+        else:
+            self.flat_p = arena.take(n, torch.float32)
+            self.flat_g = arena.take(n, torch.float32)
         self.flat_m = torch.zeros(n, device=dev, dtype=torch.float32)
+        self.shard = (0, n)                             # [lo, hi) of the flat buffers this rank updates
+        self.per_rank = n
         self.flat_hi = self.flat_lo = None          # bf16 pairs of the parameters, written by the fused update (presplit)
-        self.touched = [False] * len(params)
+        self.touched = [False] * len(params)            # parameters the update covers (agreed across ranks)
+        self.local_touched = [False] * len(params)      # ... that THIS rank's autograd has ever reached
         with torch.no_grad():
             for p, o in zip(params, offs):
                 view = self.flat_p[o:o + p.numel()].view_as(p)
@@ -79,10 +144,15 @@ class FlatGroup(object):
         if cur:
             self.chunks.append((start, self.n, cur))
 
-    def touched_ranges(self):
-        """Contiguous [a, b) runs of the flat buffer covering the parameters that have ever had a gradient."""
+    def shard_of(self, rank):
+        return (min(self.n, rank * self.per_rank), min(self.n, (rank + 1) * self.per_rank))
+
+    def touched_ranges(self, want=True):
+        """Contiguous [a, b) runs of the flat buffer covering the parameters that have ever had a gradient
+        (want=False: the complement)."""
         runs, a = [], None
         for i, t in enumerate(self.touched):
+            t = (t == want)
             if t and a is None:
                 a = self.offs[i]
             if not t and a is not None:
@@ -97,7 +167,7 @@ class FlatSGD(torch.optim.Optimizer):
     default). momentum / weight_decay / max_norm shared (train_rels.py:66,145)."""
 
     def __init__(self, groups, lr=None, momentum=0.9, weight_decay=1e-4, max_norm=5.0, overlap_comm=True,
-                 chunk_bytes=128 << 20, defer_step=False, presplit=True):
+                 chunk_bytes=128 << 20, defer_step=False, presplit=True, comm="auto"):
         pgs = []
         for g in groups:
             if isinstance(g, dict):
@@ -111,13 +181,44 @@ class FlatSGD(torch.optim.Optimizer):
                 raise ValueError("FlatSGD: a group has no learning rate")
             pgs.append({'params': ps, 'lr': float(glr)})
         super().__init__(pgs, dict(lr=0.0, momentum=momentum, weight_decay=weight_decay, max_norm=max_norm))
-        self.groups = [FlatGroup(pg['params'], chunk_bytes) for pg in self.param_groups]
+        import os as _os
+        self._device = pgs[0]['params'][0].device
+        self._distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        self._presplit = bool(presplit) and self._device.type == "cuda"
+        # ---- communication mode (module docstring): "nvls" = sharded update through NVSwitch multicast, "nccl" = all-reduce
+        comm = _os.environ.get("MOTIFS_DP_COMM", comm)
+        if comm not in ("auto", "ce", "nvls", "nccl"):
+            raise ValueError("FlatSGD: comm must be 'auto', 'ce', 'nvls' or 'nccl'")
+        self._arena = None
+        if self._distributed and self._device.type == "cuda" and comm in ("auto", "ce", "nvls"):
+            world = dist.get_world_size()
+            sizes = [flat_size(pg['params']) for pg in pgs]
+            per = 8 + (4 if self._presplit else 0) + 4                   # p + g (+ hi + lo) + staging, bytes per element
+            try:
+                self._arena = SymmArena(sum(n * per + 8 * 256 + 128 * world for n in sizes) + 8 * world + 256, self._device)
+                if comm == "nvls" and not self._arena.mc_base:
+                    raise RuntimeError("symmetric memory without multicast support")
+            except Exception as e:                                       # noqa: no symmetric memory / multicast here
+                if comm != "auto":
+                    raise
+                import warnings
+                warnings.warn("FlatSGD: symmetric memory unavailable (%r); using the NCCL all-reduce" % (e,))
+                self._arena = None
+        self.comm = ("nvls" if comm == "nvls" else "ce") if self._arena is not None else ("nccl" if self._distributed else "none")
+        self.groups = [FlatGroup(pg['params'], chunk_bytes, self._arena) for pg in self.param_groups]
         self.momentum, self.weight_decay, self.max_norm = momentum, weight_decay, max_norm
         self.steps = 0
-        self._device = self.groups[0].flat_p.device
         tc_ops.bump_weight_epoch()       # storages moved
-        self._distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
-        self._overlap = self._distributed and overlap_comm
+        self._overlap = self._distributed and overlap_comm and self.comm == "nccl"
+        self._sharded = self.comm in ("ce", "nvls")
+        if self.comm in ("ce", "nvls"):
+            world, rank = dist.get_world_size(), dist.get_rank()
+            for g in self.groups:                                        # shard boundaries: multiples of 32 elements
+                g.per_rank = ((g.n + world - 1) // world + 31) // 32 * 32
+                g.shard = g.shard_of(rank)
+                # landing area for the other ranks' copies of my shard (copy-engine reduce-scatter)
+                g.stage = self._arena.take((world - 1) * g.per_rank, torch.float32) if self.comm == "ce" else None
+            self._slots = self._arena.take(world, torch.float64)         # the ranks' partial squared norms
         # fixed collective order: the groups last in `groups` first, inside a group the last chunk first —
         # roughly the order backward produces them (late layers first), identical on every rank by construction
         self._order = [(gi, ci) for gi in reversed(range(len(self.groups)))
@@ -129,15 +230,22 @@ class FlatSGD(torch.optim.Optimizer):
         self._pending_ev = None
         self._reduced = False
         self._reserved = False
-        import os as _os
-        self._sm_reserve = int(_os.environ.get("MOTIFS_NCCL_SM_RESERVE", "16")) if self._distributed else 0
+        self._sm_reserve = int(_os.environ.get("MOTIFS_NCCL_SM_RESERVE", "0")) if self._distributed else 0
         # presplit: the update kernel also writes the bf16 (hi, lo) pair of every updated parameter (+2 x 2 B per parameter);
         # weight matrices whose rows are a multiple of 64 long hand those views to lib/tc_ops as their GEMM operand
-        self._presplit = bool(presplit) and self._device.type == "cuda"
         if self._presplit:
             for g in self.groups:
-                g.flat_hi = torch.zeros(g.n, device=self._device, dtype=torch.bfloat16)
-                g.flat_lo = torch.zeros(g.n, device=self._device, dtype=torch.bfloat16)
+                if self._arena is not None:
+                    g.flat_hi = self._arena.take(g.n, torch.bfloat16)
+                    g.flat_lo = self._arena.take(g.n, torch.bfloat16)
+                else:
+                    g.flat_hi = torch.zeros(g.n, device=self._device, dtype=torch.bfloat16)
+                    g.flat_lo = torch.zeros(g.n, device=self._device, dtype=torch.bfloat16)
+        if self._defer and _os.environ.get("MOTIFS_OPTIM_BACKGROUND", "0") == "1":
+            # opt-in: launch the deferred kernels in the shape that fits BESIDE a tcgen05 GEMM CTA (csrc/optim.cu). Measured
+            # (profiles/r02_trace_gaps_bg.log): the 1 ms hole in the compute stream closes, but the co-resident GEMMs slow
+            # down by more than that (14.7 vs 12.8 ms busy) and the update itself takes 4x longer — 18.1 vs 17.1 ms/step.
+            _c.load().mb200_optim_set_background(1)
         self._acc = torch.zeros(1, dtype=torch.float64, device=self._device)
         self._total = torch.zeros(1, dtype=torch.float32, device=self._device)
         # One hook per parameter. (1) It marks the parameter's flat gradient as touched by autograd, which ends
@@ -208,6 +316,9 @@ class FlatSGD(torch.optim.Optimizer):
         here in the same fixed order. Without `defer_step` this also waits for them."""
         if not self._distributed:
             return
+        self._reduced = True
+        if self._sharded:                # the exchange is part of the update (`_update_ce` / `_update_nvls`)
+            return
         if self._overlap:
             self._launch_ready(force=True)
         else:
@@ -224,13 +335,139 @@ class FlatSGD(torch.optim.Optimizer):
 
     # ------------------------------------------------------------------ update
     def _mark_touched(self):
+        changed = False
         for g in self.groups:
             for i, p in enumerate(g.params):
                 st = p._mb200_direct
-                if st.dirty or st.written:
-                    g.touched[i] = True
+                if (st.dirty or st.written) and not g.local_touched[i]:
+                    g.local_touched[i] = True
+                    changed = True
+        if not self._distributed:
+            for g in self.groups:
+                g.touched = list(g.local_touched)
+            return
+        # Data parallel: WHICH parameters the update covers must be the same on every rank, or the replicas drift apart
+        # (a parameter one rank's graph never reaches would be updated on the others only). The flags are agreed by a MAX
+        # all-reduce — on steps 0-2, when the set is being discovered, and every 64th step after that (it costs a host
+        # read-back, so not every step). A parameter first touched in between joins the update at the next agreement; its
+        # gradient up to then is dropped on every rank alike (`_update` zeroes the ranges outside the agreed set).
+        if self.steps < 3 or self.steps % 64 == 0:
+            flags = torch.tensor([1 if t else 0 for g in self.groups for t in g.local_touched], dtype=torch.int32)
+            flags = flags.to(self._device)
+            dist.all_reduce(flags, op=dist.ReduceOp.MAX)
+            flags = flags.cpu().tolist()
+            k = 0
+            for g in self.groups:
+                g.touched = [bool(f) for f in flags[k:k + len(g.params)]]
+                k += len(g.params)
+
+    def _shard_ranges(self, g, want=True):
+        lo, hi = g.shard
+        return [(max(a, lo), min(b, hi)) for a, b in g.touched_ranges(want) if min(b, hi) > max(a, lo)]
+
+    def _update_nvls(self):
+        """The sharded update over NVSwitch multicast (module docstring): barrier, reduce own shard + norm, barrier,
+        clip + SGD on the own shard with multicast stores, barrier. All on the current stream."""
+        lib, ar = _c.load(), self._arena
+        world, rank = dist.get_world_size(), dist.get_rank()
+        inv = 1.0 / world
+        with torch.cuda.device(self._device):
+            ar.barrier()                                   # A: every rank's gradients are final
+            self._acc.zero_()
+            for g in self.groups:
+                lo, hi = g.shard
+                if hi > lo:
+                    sh = g.flat_g[lo:hi]
+                    _c.check(lib.mb200_dp_reduce_shard_sumsq(ar.mc(sh), _c.ptr(sh), hi - lo, _c.ptr(self._acc), _c.cur_stream()),
+                             "mb200_dp_reduce_shard_sumsq")
+            _c.check(lib.mb200_dp_bcast_slot(_c.ptr(self._acc), ar.mc(self._slots), rank, _c.cur_stream()), "mb200_dp_bcast_slot")
+            ar.barrier()                                   # B: all partial norms are in; nobody reads my gradients any more
+            torch.sum(self._slots, dim=0, keepdim=True, out=self._acc)     # same order on every rank: identical clip factor
+            torch.mul(self._acc.sqrt(), inv, out=self._acc)
+            self._total.copy_(self._acc)                   # norm of the AVERAGED gradient
+            first = 1 if self.steps == 0 else 0
+            for g, pg in zip(self.groups, self.param_groups):
+                lo, hi = g.shard
+                for a, b in ((0, lo), (hi, g.n)):           # my copies of the other ranks' shards: zero for the next backward
+                    if b > a:
+                        _c.check(lib.mb200_zero_async(_c.ptr(g.flat_g[a:b]), (b - a) * 4, _c.cur_stream()), "mb200_zero_async")
+                for a, b in self._shard_ranges(g):
+                    rc = lib.mb200_sgd_momentum_clip_mc(
+                        _c.ptr(g.flat_p[a:b]), _c.ptr(g.flat_g[a:b]), _c.ptr(g.flat_m[a:b]), ar.mc(g.flat_p[a:b]),
+                        ar.mc(g.flat_hi[a:b]) if self._presplit else None, ar.mc(g.flat_lo[a:b]) if self._presplit else None,
+                        b - a, float(pg['lr']), float(pg.get('momentum', self.momentum)),
+                        float(pg.get('weight_decay', self.weight_decay)), _c.ptr(self._total), float(self.max_norm), float(inv),
+                        first, 1, _c.cur_stream())
+                    _c.check(rc, "mb200_sgd_momentum_clip_mc")
+                for a, b in self._shard_ranges(g, want=False):     # outside the agreed set: nothing applied, nothing piles up
+                    _c.check(lib.mb200_zero_async(_c.ptr(g.flat_g[a:b]), (b - a) * 4, _c.cur_stream()), "mb200_zero_async")
+            ar.barrier()                                   # C: every rank's parameter stores have landed everywhere
+        self._reduced = False
+
+    def _update_ce(self):
+        """Sharded update with COPY-ENGINE transport over NVLink (module docstring). The only kernels are local and
+        shard-sized; every byte that crosses NVSwitch is moved by a DMA engine into peer-mapped symmetric memory."""
+        lib, ar = _c.load(), self._arena
+        world, rank = dist.get_world_size(), dist.get_rank()
+        inv = 1.0 / world
+        order = [(rank + k) % world for k in range(1, world)]       # staggered: at any moment every rank has one sender
+        with torch.cuda.device(self._device):
+            # 1. reduce-scatter: my copy of rank q's shard -> my slot of q's landing area
+            for q in order:
+                slot = (rank - q - 1) % world
+                for g in self.groups:
+                    lo, hi = g.shard_of(q)
+                    if hi > lo:
+                        dst = ar.peer_view(q, g.stage)[slot * g.per_rank: slot * g.per_rank + (hi - lo)]
+                        dst.copy_(g.flat_g[lo:hi], non_blocking=True)
+            ar.barrier()                                   # A: every copy of my shard has landed here
+            self._acc.zero_()
+            for g in self.groups:
+                lo, hi = g.shard
+                if hi > lo:
+                    _c.check(lib.mb200_dp_reduce_staged_sumsq(_c.ptr(g.flat_g[lo:hi]), _c.ptr(g.stage), g.per_rank, world - 1,
+                                                              hi - lo, _c.ptr(self._acc), _c.cur_stream()),
+                             "mb200_dp_reduce_staged_sumsq")
+            self._slots[rank:rank + 1].copy_(self._acc, non_blocking=True)
+            for q in order:                                # the W partial squared norms, 8 bytes each
+                ar.peer_view(q, self._slots)[rank:rank + 1].copy_(self._acc, non_blocking=True)
+            ar.barrier()                                   # B: all partial norms are in
+            torch.sum(self._slots, dim=0, keepdim=True, out=self._acc)     # same order on every rank: identical clip factor
+            torch.mul(self._acc.sqrt(), inv, out=self._acc)
+            self._total.copy_(self._acc)                   # norm of the AVERAGED gradient
+            first = 1 if self.steps == 0 else 0
+            for g, pg in zip(self.groups, self.param_groups):
+                lo, hi = g.shard
+                for a, b in ((0, lo), (hi, g.n)):           # my copies of the other ranks' shards: zero for the next backward
+                    if b > a:
+                        _c.check(lib.mb200_zero_async(_c.ptr(g.flat_g[a:b]), (b - a) * 4, _c.cur_stream()), "mb200_zero_async")
+                for a, b in self._shard_ranges(g):
+                    args = (b - a, float(pg['lr']), float(pg.get('momentum', self.momentum)),
+                            float(pg.get('weight_decay', self.weight_decay)), _c.ptr(self._total), float(self.max_norm),
+                            float(inv), first, 1, _c.cur_stream())
+                    if self._presplit:
+                        rc = lib.mb200_sgd_momentum_clip_split(_c.ptr(g.flat_p[a:b]), _c.ptr(g.flat_g[a:b]), _c.ptr(g.flat_m[a:b]),
+                                                               _c.ptr(g.flat_hi[a:b]), _c.ptr(g.flat_lo[a:b]), *args)
+                    else:
+                        rc = lib.mb200_sgd_momentum_clip_scaled(_c.ptr(g.flat_p[a:b]), _c.ptr(g.flat_g[a:b]), _c.ptr(g.flat_m[a:b]), *args)
+                    _c.check(rc, "mb200_sgd_momentum_clip")
+                for a, b in self._shard_ranges(g, want=False):     # outside the agreed set: nothing applied, nothing piles up
+                    _c.check(lib.mb200_zero_async(_c.ptr(g.flat_g[a:b]), (b - a) * 4, _c.cur_stream()), "mb200_zero_async")
+            # 3. all-gather: my updated shard (parameters + operand pairs) -> the same place in every other arena
+            for q in order:
+                for g in self.groups:
+                    lo, hi = g.shard
+                    if hi > lo:
+                        for buf in ((g.flat_p, g.flat_hi, g.flat_lo) if self._presplit else (g.flat_p,)):
+                            ar.peer_view(q, buf)[lo:hi].copy_(buf[lo:hi], non_blocking=True)
+            ar.barrier()                                   # C: every rank's shard has landed everywhere
+        self._reduced = False
 
     def _update(self):
+        if self.comm == "nvls":
+            return self._update_nvls()
+        if self.comm == "ce":
+            return self._update_ce()
         lib = _c.load()
         world = dist.get_world_size() if (self._distributed and getattr(self, "_reduced", False)) else 1
         inv = 1.0 / world
@@ -257,6 +494,9 @@ class FlatSGD(torch.optim.Optimizer):
                             float(pg.get('momentum', self.momentum)), float(pg.get('weight_decay', self.weight_decay)),
                             _c.ptr(self._total), float(self.max_norm), float(inv), first, 1, _c.cur_stream())
                 _c.check(rc, "mb200_sgd_momentum_clip")
+            if self._distributed:        # outside the agreed set: nothing is applied, nothing may pile up
+                for a, b in g.touched_ranges(want=False):
+                    g.flat_g[a:b].zero_()
         self._reduced = False
 
     @torch.no_grad()
@@ -302,9 +542,14 @@ class FlatSGD(torch.optim.Optimizer):
         wait_pending_updates()
         if self._device.type == "cuda":
             torch.cuda.current_stream(self._device).synchronize()
+        moms = [g.flat_m.detach().clone() for g in self.groups]
+        if self._sharded:                # momentum exists for the own shard only: COLLECTIVE — every rank must call state_dict()
+            for g, m in zip(self.groups, moms):
+                m[:g.shard[0]].zero_(); m[g.shard[1]:].zero_()
+                dist.all_reduce(m, op=dist.ReduceOp.SUM)
         return {"steps": self.steps,
                 "param_groups": [{k: v for k, v in pg.items() if k != 'params'} for pg in self.param_groups],
-                "momentum_buffers": [g.flat_m.detach().clone() for g in self.groups],
+                "momentum_buffers": moms,
                 "touched": [list(g.touched) for g in self.groups]}
 
     def load_state_dict(self, state):
@@ -316,6 +561,9 @@ class FlatSGD(torch.optim.Optimizer):
             if m.numel() != g.n or len(t) != len(g.params):
                 raise ValueError("FlatSGD.load_state_dict: flat layout differs")
             g.flat_m.copy_(m)
+            if self._sharded:            # keep the invariant state_dict() relies on: momentum is zero outside the own shard
+                g.flat_m[:g.shard[0]].zero_(); g.flat_m[g.shard[1]:].zero_()
             g.touched = list(t)
+            g.local_touched = list(t)
             pg.update(spg)
         self.steps = int(state["steps"])

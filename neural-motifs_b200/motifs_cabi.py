@@ -67,9 +67,15 @@ SIGNATURES = {
     "mb200_anchor_targets": (c_int, [P, c_int, P, c_int, c_double, c_double, P, P, P, P, P]),
     "mb200_gemm_set_pair_mode": (c_int, [c_int]),
     "mb200_set_sm_budget": (c_int, [c_int]),
+    "mb200_zero_async": (c_int, [P, c_longlong, P]),
     "mb200_conv_set_halo_mode": (c_int, [c_int]),
     "mb200_decoder_commit": (c_int, [P, P, c_int, c_int, c_float, P, P]),
     "mb200_sgd_momentum_clip_split": (c_int, [P, P, P, P, P, c_longlong, c_float, c_float, c_float, P, c_float, c_float, c_int, c_int, P]),
+    "mb200_optim_set_background": (c_int, [c_int]),
+    "mb200_dp_reduce_shard_sumsq": (c_int, [P, P, c_longlong, P, P]),
+    "mb200_dp_bcast_slot": (c_int, [P, P, c_int, P]),
+    "mb200_dp_reduce_staged_sumsq": (c_int, [P, P, c_longlong, c_int, c_longlong, P, P]),
+    "mb200_sgd_momentum_clip_mc": (c_int, [P, P, P, P, P, P, c_longlong, c_float, c_float, c_float, P, c_float, c_float, c_int, c_int, P]),
     "mb200_highway_lstm_tc_supported": (c_int, [c_int, c_int]),
     "mb200_highway_lstm_layer_forward_tc": (c_int, [c_int, c_int, c_int, c_int, P, P, P, P, P, P, P, P, P, P, P, P]),
     "mb200_sgemm": (c_int, [c_int, c_int, c_int, c_int, c_int, c_float, P, c_int, P, c_int, c_float, P, c_int, P]),

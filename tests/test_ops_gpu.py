@@ -69,11 +69,10 @@ def test_roi_align_nhwc_matches_nchw(cuda):
     assert torch.equal(a.permute(0, 2, 3, 1).reshape(77, 49, 512), b)
 
 
-@pytest.mark.parametrize("C,ph,pw", [(512, 7, 7), (136, 7, 7), (256, 3, 5), (64, 7, 14), (128, 1, 1), (512, 8, 8)])
-def test_roi_align_nhwc_separable_edge_cases(cuda, C, ph, pw):
-    """The column-separable NHWC kernel (crop height <= 7) is bit-equal to the NCHW kernel (itself bit-equal to the
-    reference's) on whole-image, partly / fully outside, degenerate, DESCENDING and bad-batch rois; 8x8 takes the per-bin
-    kernel."""
+@pytest.mark.parametrize("C,ph,pw", [(512, 7, 7), (136, 7, 7), (256, 3, 5), (64, 7, 14), (128, 1, 1), (70, 7, 7)])
+def test_roi_align_nhwc_edge_cases(cuda, C, ph, pw):
+    """The NHWC kernels (16-byte vector path, and the scalar one for C % 4 != 0) are bit-equal to the NCHW kernel (itself
+    bit-equal to the reference's) on whole-image, partly / fully outside, degenerate, DESCENDING and bad-batch rois."""
     from lib.fpn.roi_align.functions.roi_align import RoIAlignFunction, roi_align_nhwc
     rng = np.random.RandomState(C + ph)
     feat = torch.from_numpy(rng.randn(3, C, 37, 37).astype(np.float32)).to(cuda)
@@ -99,7 +98,7 @@ def test_roi_align_backward_vs_oracle(cuda):
     B, C, N = 2, 16, 25
     feat = torch.from_numpy(rng.randn(B, C, 37, 37).astype(np.float32)).to(cuda).requires_grad_(True)
     rois = rois_for(rng, N, B)
-    rois[0, 1:] = [0, 0, 591, 591]            # window larger than the windowed backward path takes -> per-bin atomics
+    rois[0, 1:] = [0, 0, 591, 591]            # whole image
     rois[1, 1:] = [-40, -40, 100, 100]        # partly outside
     rois[2, 1:] = [300, 300, 300, 300]        # degenerate: all 49 bins on one point
     rois[3, 1:] = [400, 380, 200, 120]        # descending

@@ -75,6 +75,11 @@ def bench_roi_align(res):
         nh = timeit(lambda: lib.mb200_roi_align_forward_nhwc(C.ptr(fn), C.ptr(rn), N, B, 37, 37, 7, 7, Cn, 0.0, C.ptr(out2), st))
         row["nhwc_us_median"] = nh[0]
         row["nhwc_GBs"] = alg / nh[0] / 1e3
+        row["nhwc_frac_of_%s_hbm" % kind] = alg / nh[0] / 1e3 / pk["hbm_gbs"]
+        # the layout the pipeline consumes: NHWC feature map in, [N, C, 7, 7] out (fc6's K order)
+        nc = timeit(lambda: lib.mb200_roi_align_forward_nhwc_to_nchw(C.ptr(fn), C.ptr(rn), N, B, 37, 37, 7, 7, Cn, 0.0, C.ptr(out), st))
+        row["nhwc_to_nchw_us_median"] = nc[0]
+        row["nhwc_to_nchw_frac_of_%s_hbm" % kind] = alg / nc[0] / 1e3 / pk["hbm_gbs"]
         g = torch.randn(N, Cn, 7, 7, device=dev); gi = torch.zeros(B, Cn, 37, 37, device=dev)
         bw = timeit(lambda: lib.ROIAlignBackwardLaucher(C.ptr(g), C.ptr(rn), N, B, 37, 37, 7, 7, Cn, C.ptr(gi), st))
         row["bwd_us_median"] = bw[0]
@@ -164,11 +169,15 @@ def bench_lstm(res, quick):
 if __name__ == "__main__":
     quick = "--quick" in sys.argv
     res = {"device": torch.cuda.get_device_name(0), "peaks": peaks()[0], "peaks_kind": peaks()[1]}
+    only = [a.split("=", 1)[1] for a in sys.argv if a.startswith("--only=")]
+    outname = ([a.split("=", 1)[1] for a in sys.argv if a.startswith("--out=")] or ["microbench_ops.json"])[0]
     for name, fn in [("roi", bench_roi_align), ("nms", bench_nms), ("lstm", lambda r: bench_lstm(r, quick))]:
+        if only and name not in only:
+            continue
         try:
             fn(res)
         except Exception as e:  # keep going: partial results are still useful
             import traceback; traceback.print_exc()
             res[name + "_error"] = repr(e)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    json.dump(res, open(os.path.join(ROOT, "gpurun_out", "microbench_ops.json"), "w"), indent=1)
+    json.dump(res, open(os.path.join(ROOT, "gpurun_out", outname), "w"), indent=1)

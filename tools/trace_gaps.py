@@ -8,9 +8,15 @@ import torch
 from torch.profiler import profile, ProfilerActivity
 import bench
 from dataloaders.synthetic import make_numpy_batch, SyntheticBlob
-dev = torch.device("cuda:0")
+# under torchrun (one rank per GPU) every rank steps, rank 0 alone profiles and prints: the data-parallel timeline
+from lib.data_parallel import init_from_env
+rank, world, local = init_from_env()
+if rank != 0:
+    sys.stdout = open(os.devnull, "w")
+dev = torch.device("cuda", local)
+torch.cuda.set_device(dev)
 model = bench.build_model(dev); opt = bench.get_optim(model, 6e-3)
-blobs = [SyntheticBlob(make_numpy_batch(6, seed=i), dev) for i in range(3)]
+blobs = [SyntheticBlob(make_numpy_batch(6, seed=i + 10 * rank, image_offset=0), dev) for i in range(3)]
 for b in blobs:
     b.scatter()
 for i in range(8):
@@ -22,7 +28,7 @@ with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
         bench.train_step(model, opt, None, fwd_tuple=blobs[i % 3][0])
         torch.cuda.nvtx.range_pop()
     torch.cuda.synchronize()
-path = os.path.join(tempfile.gettempdir(), "trace.json")
+path = os.path.join(tempfile.gettempdir(), "trace_rank%d.json" % rank)
 prof.export_chrome_trace(path)
 ev = json.load(open(path))["traceEvents"]
 ks = [e for e in ev if e.get("cat") in ("kernel", "gpu_memcpy", "gpu_memset") and "dur" in e]
@@ -53,6 +59,8 @@ print("compute stream: busy %.3f ms, idle %.3f ms in %d gaps" % (busy / 1e3, sum
 other = [v for v in streams.values() if v is not main]
 for v in other:
     print("  side stream: %d events, busy %.3f ms, from %.3f to %.3f ms" % (len(v), sum(e["dur"] for e in v) / 1e3, (v[0]["ts"] - a) / 1e3, (v[-1]["ts"] + v[-1]["dur"] - a) / 1e3))
+    for e in sorted(v, key=lambda e: -e["dur"])[:12]:
+        print("      %8.1f us @ %6.2f ms  %s" % (e["dur"], (e["ts"] - a) / 1e3, e["name"][:70]))
 gaps.sort(reverse=True)
 print("largest gaps (us, at ms into the step):")
 for g in gaps[:25]:
