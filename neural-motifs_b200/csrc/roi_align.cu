@@ -350,6 +350,9 @@ roi_align_fwd_nhwc_kernel(const float* __restrict__ feat, const float* __restric
 // corner loads for 103 MB of output), so 35-60 % fewer loads looked like the lever; measured it was 2.3x SLOWER (78.8 vs
 // 34.8 us at N=1024): 80-128 registers for the row cache leave 14 warps per SM, and the dependent emission loop after the
 // load batch exposes latency the per-bin kernel hides with 24 warps x 16 independent loads.
+// Also tried and removed: a WARP-AUTONOMOUS prologue (every warp samples both axes itself and reads the bin descriptors with
+// shuffles: no shared tables, no block barrier in front of the loads) — 40.0 vs 35.9 us bin-major, 49.1 vs 49.2 us in the
+// [N,C,7,7] layout (gpurun call of 2026-09-23, tools/run_roi.py): the prologue is not what bounds the kernel either.
 
 // scalar NHWC fallback for channel counts that are not a multiple of 4
 __global__ void __launch_bounds__(kThreads)

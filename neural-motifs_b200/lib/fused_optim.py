@@ -22,26 +22,27 @@ chunk order on every rank (chunk k goes out only after every chunk before it in 
 that skipped backward) still issue identical collective sequences. One backward per `all_reduce_grads()`; a second
 backward after a chunk has gone out raises (it would add local gradients to an already averaged chunk).
 
-`defer_step=True` (opt-in): `step()` enqueues [wait for the all-reduce, norm, fused update] on a side stream and
-returns at once; the next forward's frozen backbone (9 of 21 ms) runs underneath it and `wait_pending_updates()`
-— called by RelModel / ObjectDetector.forward before the first trainable parameter is read — joins the two
-streams. The gradient all-reduce is then off the critical path entirely at any world size.
+`defer_step=True` (opt-in): `step()` enqueues [exchange, norm, fused update] on a side stream and returns at once; the
+next forward's frozen backbone (5 of 17 ms) is queued meanwhile and `wait_pending_updates()` — called by RelModel /
+ObjectDetector.forward before the first trainable parameter is read — joins the two streams. The data movement of the
+exchange hides underneath the backbone; the update KERNELS do not (a tcgen05 GEMM CTA needs an SM to itself: the GEMMs wait
+for them, ~1 ms at one GPU, 1/W of that sharded), see DESIGN.md section 4.
 
-Data parallel over NVSwitch (`comm="nvls"`, the default on CUDA when torch's symmetric-memory rendezvous offers multicast):
-gradients, parameters and their bf16 operand pairs live in ONE symmetric allocation per optimizer; each rank owns a
-contiguous shard of every flat buffer and the step is three of our own kernels (csrc/optim.cu) between device-side barriers:
-  barrier A  every rank's backward has finished
-  pass 1     `multimem.ld_reduce.add` of the own shard: the switch returns the sum over all ranks -> local gradient shard,
-             and its squared norm (reduce-scatter + norm, no staging copy); the W partial norms are multicast to all ranks
-  barrier B
-  pass 2     fused clip + SGD on the own shard; the new parameters and operand pairs leave through `multimem.st`, which
-             lands them in EVERY rank's copy (the all-gather is the store)
-  barrier C
-No NCCL kernel takes part: NCCL's 32 channel CTAs cannot share an SM with a 200 KB / 54 K-register tcgen05 GEMM CTA, so an
-all-reduce underneath the backbone pushed the persistent GEMMs into a second wave (+1.4 ms per step at 2 GPUs, profiles/
-r02_nccl_channels.json, r02_trace_gaps_n2.log). The passes launch in the BACKGROUND shape (one 128-thread CTA per SM) that
-does fit beside a GEMM CTA. Momentum exists for the own shard only. `comm="nccl"` keeps the chunked all-reduce (the CPU /
-gloo tests, GPUs without multicast)."""
+Data parallel over NVSwitch: a SHARDED update in peer memory instead of an all-reduce. Gradients, parameters, their bf16
+operand pairs and a landing area live in ONE symmetric allocation per optimizer (torch's symmetric memory does the plumbing:
+cuMem allocation, peer + multicast mapping, device-side barrier); each rank owns a contiguous shard of every flat buffer.
+`comm="ce"` (default on CUDA when the rendezvous succeeds) — transport by COPY ENGINE, the SMs only see local, shard-sized work:
+  1  my copy of rank q's gradient shard -> my slot of q's landing area (cudaMemcpyAsync into the peer mapping)   | barrier
+  2  own shard += the W-1 landed copies, and its squared norm (one kernel); the W partial norms are exchanged     | barrier
+  3  fused clip + SGD on the own shard only (1/W of the update's HBM traffic; momentum exists for the own shard only)
+  4  the updated shard (parameters + operand pairs) -> the same place in every other arena, copy engines          | barrier
+`comm="nvls"` — the same with the transport inside our kernels (csrc/optim.cu): `multimem.ld_reduce.add` of the own shard (the
+switch returns the sum over all ranks) in step 2, `multimem.st` (one store lands in every rank's copy) in step 3.
+Why not NCCL (`comm="nccl"`, kept as the fallback and for the gloo CPU tests): its 32 channel CTAs cannot share an SM with a
+200 KB / 54 K-register tcgen05 GEMM CTA, so an all-reduce underneath the backbone takes SMs away from the persistent GEMMs
+(2 GPUs: 18.3 ms/step against 17.8 with comm="ce"; profiles/r02_bench_n2_*.json), and fewer channels cannot carry 1.1 GB in
+time (profiles/r02_nccl_channels.json). Parameters are bit-identical on all ranks by construction (one owner per element).
+tools/check_dp_sharded.py checks both modes against clip + torch SGD on NCCL-averaged gradients on 2 and 4 GPUs."""
 import torch
 import torch.distributed as dist
 
