@@ -312,3 +312,68 @@ def test_bench_settle_warmup_leaves_collectively_gloo_world2():
     out = mgr.dict()
     mp.spawn(_worker_settle, args=(2, _free_port(), out), nprocs=2, join=True)
     assert out[0] == out[1] and 6 <= out[0][0] <= 40
+
+
+def _worker_touched(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "neural-motifs_b200"))
+    from lib.data_parallel import init_from_env
+    from lib.fused_optim import FlatSGD
+    init_from_env("gloo")
+    torch.manual_seed(0)
+    ps = [torch.nn.Parameter(torch.randn(n)) for n in (40, 7, 300, 12)]
+    opt = FlatSGD([(ps[:2], 0.01), (ps[2:], 0.1)], comm="nccl")
+    # rank 0's graph reaches parameters 0 and 2, rank 1's reaches 0 and 1; nobody reaches 3
+    used = [0, 2] if rank == 0 else [0, 1]
+    sum((ps[i] * 2.0).sum() for i in used).backward()
+    opt._mark_touched()                                    # what step() does first; the fused kernels need a GPU
+    out[rank] = ([list(g.local_touched) for g in opt.groups], [list(g.touched) for g in opt.groups],
+                 [g.touched_ranges() for g in opt.groups], [g.touched_ranges(want=False) for g in opt.groups])
+    dist.destroy_process_group()
+
+
+def test_touched_parameter_set_is_agreed_across_ranks():
+    """Which parameters the fused update covers must not depend on the rank (lib/fused_optim.FlatSGD._mark_touched): the
+    union of what any rank's autograd has reached, the same ranges everywhere; what nobody reached stays out (torch's
+    `grad is None` skip)."""
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker_touched, args=(2, _free_port(), out), nprocs=2, join=True)
+    assert out[0][0] == [[True, False], [True, False]] and out[1][0] == [[True, True], [False, False]]     # local
+    assert out[0][1] == out[1][1] == [[True, True], [True, False]]                                          # agreed
+    assert out[0][2] == out[1][2] == [[(0, 48)], [(0, 300)]]          # 40 + 7 padded to multiples of 4; 300
+    assert out[0][3] == out[1][3] == [[], [(300, 312)]]
+
+
+def test_shard_layout_partitions_every_flat_buffer():
+    """The sharded update (comm="ce" / "nvls"): rank r owns [r * per_rank, (r + 1) * per_rank) of each flat buffer, in
+    multiples of 32 elements; the shards are disjoint, cover the buffer, and a parameter range is split across owners
+    exactly at those boundaries (FlatGroup.shard_of, FlatSGD._shard_ranges)."""
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "neural-motifs_b200"))
+    from lib.fused_optim import FlatGroup, FlatSGD
+    ps = [torch.nn.Parameter(torch.zeros(n)) for n in (1000, 37, 4096, 5, 130)]
+    for world in (2, 3, 4, 8):
+        g = FlatGroup(ps)
+        g.per_rank = ((g.n + world - 1) // world + 31) // 32 * 32
+        shards = [g.shard_of(r) for r in range(world)]
+        assert shards[0][0] == 0 and shards[-1][1] == g.n
+        assert all(a[1] == b[0] for a, b in zip(shards, shards[1:]))                        # contiguous, disjoint
+        assert all(lo % 32 == 0 and (hi % 4 == 0) for lo, hi in shards)
+        g.touched = [True, False, True, True, False]
+        covered = []
+        for r in range(world):
+            g.shard = shards[r]
+            covered += FlatSGD._shard_ranges(None, g)
+            assert all(lo % 4 == 0 and hi % 4 == 0 for lo, hi in FlatSGD._shard_ranges(None, g, want=False))
+        covered.sort()
+        merged = [list(covered[0])]
+        for a, b in covered[1:]:
+            if a == merged[-1][1]:
+                merged[-1][1] = b
+            else:
+                merged.append([a, b])
+        assert [tuple(m) for m in merged] == g.touched_ranges()                             # the union is the touched set
