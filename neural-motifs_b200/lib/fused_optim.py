@@ -186,7 +186,7 @@ class FlatSGD(torch.optim.Optimizer):
         self._device = pgs[0]['params'][0].device
         self._distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
         self._presplit = bool(presplit) and self._device.type == "cuda"
-        # ---- communication mode (module docstring): "nvls" = sharded update through NVSwitch multicast, "nccl" = all-reduce
+        # ---- communication mode (module docstring): "ce" / "nvls" = sharded update over NVSwitch peer memory, "nccl" = all-reduce
         comm = _os.environ.get("MOTIFS_DP_COMM", comm)
         if comm not in ("auto", "ce", "nvls", "nccl"):
             raise ValueError("FlatSGD: comm must be 'auto', 'ce', 'nvls' or 'nccl'")
@@ -267,9 +267,10 @@ class FlatSGD(torch.optim.Optimizer):
         self._next = 0               # index into self._order of the next chunk to launch
 
     def _reserve_sms(self, on):
-        """While chunk all-reduces are in flight NCCL's channel CTAs hold SMs: the persistent tcgen05 kernels queued in that
-        window (rest of backward, the next step's backbone) get a grid that leaves `nccl_sm_reserve` SMs free, else their
-        last CTAs would run in a second wave behind NCCL's (measured at 2 GPUs: +1.6 ms per step)."""
+        """comm="nccl", opt-in (MOTIFS_NCCL_SM_RESERVE=n, default 0): while chunk all-reduces are in flight NCCL's channel CTAs
+        hold SMs, so the persistent tcgen05 kernels queued in that window get a grid that leaves n SMs free instead of running
+        their last CTAs in a second wave. Measured at 2 GPUs it does not pay (18.85 ms/step without, 19.25 with n = 32): the
+        host cannot know when the collective ends, so the narrower grid covers the whole backbone."""
         if self._device.type != "cuda" or self._sm_reserve <= 0 or on == self._reserved:
             return
         _c.load().mb200_set_sm_budget(148 - self._sm_reserve if on else 148)
@@ -336,13 +337,11 @@ class FlatSGD(torch.optim.Optimizer):
 
     # ------------------------------------------------------------------ update
     def _mark_touched(self):
-        changed = False
         for g in self.groups:
             for i, p in enumerate(g.params):
                 st = p._mb200_direct
-                if (st.dirty or st.written) and not g.local_touched[i]:
+                if st.dirty or st.written:
                     g.local_touched[i] = True
-                    changed = True
         if not self._distributed:
             for g in self.groups:
                 g.touched = list(g.local_touched)
